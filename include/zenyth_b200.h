@@ -1,0 +1,188 @@
+/* zenyth_b200.h — C ABI of the B200-native scene-update path for the Zenyth engine.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, integer status codes, no C++ or
+ * torch types.  The upstream engine (TNtube/Zenyth) has no FFI and no implementation of this
+ * path; its only plugin seam is Zenyth::IRenderer (Core/include/IRenderer.hpp:5-12) and the
+ * frame hooks Application::OnUpdate / OnRender (Core/include/Application.hpp:38-39, driven by
+ * Core/src/Application.cpp:41-52).  Each entry point below names the reference declaration it
+ * stands in for or would be called from.  include/zenyth_b200.hpp layers the engine-idiom C++
+ * types (Zenyth::Transform / Scene / Camera / Mesh) on top of these calls; INTEGRATION.md shows
+ * the binding a maintainer adds on the reference side.
+ *
+ * Conventions (DESIGN.md "Conventions"): matrices are 16 floats, column-major, element (r,c) at
+ * [c*4+r], translation in [12..14]  (Core/include/math/matrix.hpp:7-8,57-58); right-handed;
+ * column vectors (matrix.hpp:50); angles in radians (Core/include/math/utils.hpp:5); clip depth
+ * 0..1.  Entities are level-ordered: every parent index is smaller than its children's and
+ * level l is the index range [level_offsets[l], level_offsets[l+1]).
+ *
+ * Errors: every call returns ZN_OK (0) or a ZN_ERR_* code and never throws; zn_last_error()
+ * returns the calling thread's last message.  (The reference's convention is
+ * std::runtime_error on set-up failure, Core/src/Application.cpp:28-30; the C++ wrapper
+ * rethrows.)  Threading: one host thread per context at a time, one context per GPU.  There is
+ * no CPU fallback: without a usable sm_100 device zn_ctx_create fails with ZN_ERR_NO_DEVICE.
+ */
+#ifndef ZENYTH_B200_H
+#define ZENYTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZN_ABI_VERSION 1
+
+#define ZN_OK 0
+#define ZN_ERR_INVALID 1   /* bad argument */
+#define ZN_ERR_CUDA 2      /* a CUDA runtime / driver call failed */
+#define ZN_ERR_NO_DEVICE 3 /* no CUDA device, or not compute capability 10.x */
+#define ZN_ERR_STATE 4     /* call order (e.g. update before a camera was set) */
+#define ZN_ERR_NOMEM 5
+
+#define ZN_NO_PARENT 0xFFFFFFFFu
+
+typedef struct zn_ctx zn_ctx;
+typedef struct zn_scene zn_scene;
+typedef struct zn_mesh zn_mesh;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int zn_abi_version(void);
+const char* zn_last_error(void);
+int zn_device_count(int* out_count);
+
+/* ---- context: one per GPU.  Stands where IRenderer::Init / destructor sit
+ *      (Core/include/IRenderer.hpp:7-8; lifetime per Core/src/Application.cpp:32-34,54-56). ---- */
+int zn_ctx_create(int device_ordinal, zn_ctx** out_ctx);
+int zn_ctx_destroy(zn_ctx* ctx);
+/* All work of this context is enqueued on `cuda_stream` (a cudaStream_t / CUstream passed as
+ * void*); NULL restores the context's own stream. */
+int zn_ctx_set_stream(zn_ctx* ctx, void* cuda_stream);
+int zn_ctx_get_stream(zn_ctx* ctx, void** out_cuda_stream);
+int zn_ctx_sync(zn_ctx* ctx);
+int zn_ctx_sm_count(zn_ctx* ctx, int* out_sm_count);
+/* Page-locked host memory for the *_host entry points (plain malloc memory also works, slower). */
+int zn_host_alloc(zn_ctx* ctx, size_t bytes, void** out_ptr);
+int zn_host_free(zn_ctx* ctx, void* ptr);
+
+/* ---- camera maths: the part of mat4 a Camera needs, completing the stubs
+ *      mat4::look_at / perspective / orthographic / perspective_reverse_z / operator*
+ *      (Core/include/math/matrix.hpp:32,52-55; stub bodies Core/src/math/matrix.cpp:55-57,107-121).
+ *      Host-side, pure functions. ---- */
+void zn_mat4_look_at(const float eye[3], const float center[3], const float up[3], float out[16]);
+void zn_mat4_perspective(float fov_y_rad, float aspect, float near_z, float far_z, float out[16]);
+void zn_mat4_orthographic(float left, float right, float bottom, float top, float near_z, float far_z, float out[16]);
+void zn_mat4_perspective_reverse_z(float fov_y_rad, float aspect, float near_z, float out[16]);
+void zn_mat4_mul(const float a[16], const float b[16], float out[16]);
+/* Six planes (nx,ny,nz,d) from the rows of view_proj: left,right,bottom,top,near,far. */
+void zn_frustum_planes(const float view_proj[16], float out_planes[24]);
+
+/* ---- scene: TRS -> world over the hierarchy, MVP, AABB-vs-frustum cull + ordered compaction.
+ *      Called from where Application::OnUpdate(dt) and OnRender() run
+ *      (Core/src/Application.cpp:47,50). ---- */
+typedef struct zn_scene_desc {
+	uint32_t entity_count;
+	uint32_t level_count;          /* >= 1 */
+	const uint32_t* level_offsets; /* [level_count+1], level_offsets[0]==0, last==entity_count;
+	                                  NULL means one level of roots */
+} zn_scene_desc;
+
+int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene);
+int zn_scene_destroy(zn_scene* scene);
+
+/* Host -> device upload of entities [first, first+count).  Each array is `count` records of
+ * three floats, `stride_bytes` apart (12 for packed float[3], 16 for arrays of the reference's
+ * 16-byte zenyth::math::vec3, Core/include/math/vector.hpp:69-72).  NULL arrays are skipped.
+ * rotation = (pitch, yaw, roll) radians as mat4::from_euler (matrix.hpp:24). */
+int zn_scene_set_transforms(zn_scene* scene, uint32_t first, uint32_t count,
+                            const float* position, const float* rotation, const float* scale, size_t stride_bytes);
+int zn_scene_set_bounds(zn_scene* scene, uint32_t first, uint32_t count,
+                        const float* aabb_center, const float* aabb_half_extent, size_t stride_bytes);
+/* parent[i] is an entity index in an earlier level, or ZN_NO_PARENT.  Level 0 must be all roots. */
+int zn_scene_set_parents(zn_scene* scene, uint32_t first, uint32_t count, const uint32_t* parent);
+/* view and proj exactly as mat4::data() (matrix.hpp:60-61). */
+int zn_scene_set_camera(zn_scene* scene, const float view[16], const float proj[16]);
+/* Added to every index written to the visible list (shard -> global numbering). */
+int zn_scene_set_index_base(zn_scene* scene, uint32_t index_base);
+
+/* One frame, asynchronous on the context stream: world[E], mvp[E], visible list + count. */
+int zn_scene_update(zn_scene* scene);
+
+/* Results.  These synchronise the stream. */
+int zn_scene_visible_count(zn_scene* scene, uint32_t* out_count);
+int zn_scene_read_visible(zn_scene* scene, uint32_t* out_indices, uint32_t capacity, uint32_t* out_count);
+int zn_scene_read_world(zn_scene* scene, uint32_t first, uint32_t count, float* out_matrices);
+int zn_scene_read_mvp(zn_scene* scene, uint32_t first, uint32_t count, float* out_matrices);
+int zn_scene_read_inputs(zn_scene* scene, uint32_t first, uint32_t count,
+                         float* position, float* rotation, float* scale,
+                         float* aabb_center, float* aabb_half_extent, uint32_t* parent); /* packed [count][3] */
+
+/* Device-resident results for a renderer or a collective to consume in place. */
+typedef struct zn_scene_buffers {
+	void* world;            /* float[E][16] */
+	void* mvp;              /* float[E][16] */
+	void* visible;          /* uint32[E], first *visible_count entries valid, ascending */
+	void* visible_count;    /* uint32[1] */
+	uint32_t entity_count;
+} zn_scene_buffers;
+int zn_scene_device_buffers(zn_scene* scene, zn_scene_buffers* out);
+
+/* End-to-end frame with HOST buffers: uploads the packed [E][3] inputs (NULL = keep what is
+ * resident), runs the frame, downloads what is asked for (NULL = leave on the device), and
+ * returns after the data has landed.  This is the call a CPU engine would swap in. */
+typedef struct zn_frame_host_io {
+	const float* position;      /* in  [E][3] or NULL */
+	const float* rotation;      /* in  [E][3] or NULL */
+	const float* scale;         /* in  [E][3] or NULL */
+	float* world;               /* out [E][16] or NULL */
+	float* mvp;                 /* out [E][16] or NULL */
+	uint32_t* visible;          /* out [E] or NULL */
+	uint32_t visible_count;     /* out */
+} zn_frame_host_io;
+int zn_scene_frame_host(zn_scene* scene, zn_frame_host_io* io);
+
+/* Bytes one zn_scene_update moves by construction: 188 B per root entity,
+ * 192 B per child, + 4 B per visible index. */
+int zn_scene_algorithmic_bytes(zn_scene* scene, uint32_t visible_count, uint64_t* out_bytes);
+/* Number of kernel launches one zn_scene_update enqueues. */
+int zn_scene_launches_per_update(zn_scene* scene, uint32_t* out_launches);
+
+/* ---- mesh batch: bulk vertex position / normal transform by per-instance model matrices.
+ *      pos' = model.transform_point(pos); nrm' = normalize(model.inverse_transpose().transform_normal(nrm))
+ *      (Core/include/math/matrix.hpp:43-48).  The Renderer-side preprocessing that would sit
+ *      between IRenderer::BeginFrame and EndFrame (Core/include/IRenderer.hpp:9-10). ---- */
+typedef struct zn_mesh_desc {
+	uint32_t vertex_count;
+	uint32_t instance_count;
+	const uint32_t* instance_first_vertex; /* [instance_count+1], ascending, [0]==0, last==vertex_count;
+	                                          NULL means equal ranges (vertex_count % instance_count == 0) */
+} zn_mesh_desc;
+
+int zn_mesh_create(zn_ctx* ctx, const zn_mesh_desc* desc, zn_mesh** out_mesh);
+int zn_mesh_destroy(zn_mesh* mesh);
+int zn_mesh_set_vertices(zn_mesh* mesh, uint32_t first, uint32_t count,
+                         const float* position, const float* normal, size_t stride_bytes);
+int zn_mesh_set_models(zn_mesh* mesh, uint32_t first, uint32_t count, const float* model_matrices /*[count][16] host*/);
+/* Use world matrices [first_entity, first_entity+instance_count) of a scene as the models (no copy). */
+int zn_mesh_bind_scene_models(zn_mesh* mesh, zn_scene* scene, uint32_t first_entity);
+int zn_mesh_transform(zn_mesh* mesh); /* asynchronous */
+int zn_mesh_read(zn_mesh* mesh, uint32_t first, uint32_t count, float* out_position, float* out_normal); /* packed [count][3] */
+int zn_mesh_read_inputs(zn_mesh* mesh, uint32_t first, uint32_t count, float* position, float* normal);
+typedef struct zn_mesh_buffers {
+	void* position_in;  /* float[V][3] */
+	void* normal_in;
+	void* position_out;
+	void* normal_out;
+	uint32_t vertex_count;
+} zn_mesh_buffers;
+int zn_mesh_device_buffers(zn_mesh* mesh, zn_mesh_buffers* out);
+
+/* ---- synthetic inputs generated on the device (bench / test support).
+ *      A stateless hash of (seed, index, field) -> float, bit-identical to the host generator. */
+int zn_scene_fill_synthetic(zn_scene* scene, uint32_t seed, uint32_t fanout, float aabb_center_range);
+int zn_mesh_fill_synthetic(zn_mesh* mesh, uint32_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZENYTH_B200_H */

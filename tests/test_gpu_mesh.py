@@ -1,0 +1,82 @@
+"""-m gpu: the CUDA mesh vertex/normal transform, through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import rel_err, same_values
+from oracle.binding import BASE_SEED, camera
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def models_from_scene(oracle, n):
+    arrays = oracle.synth_scene(BASE_SEED + 2, [n], fanout=1)
+    arrays["parent"] = None
+    view, proj = camera(oracle)
+    return oracle.scene_update(arrays, view, proj)["world"]
+
+
+@pytest.mark.parametrize("instances,verts", [(1, 4), (3, 1024), (5, 2048), (7, 36), (64, 1000)])
+def test_uniform_instances(oracle, gpu_ctx, instances, verts):
+    import zenyth_b200 as zn
+    V = instances * verts
+    pos, nrm = oracle.synth_mesh(BASE_SEED + 4, V)
+    models = models_from_scene(oracle, instances)
+    first = (np.arange(instances + 1, dtype=np.uint32) * verts).astype(np.uint32)
+    ref_p, ref_n = oracle.mesh_transform(first, models, pos, nrm)
+    m = zn.Mesh(gpu_ctx, V, instances)
+    m.SetVertices(pos, nrm)
+    m.SetModels(models)
+    m.Transform()
+    got_p, got_n = m.Read()
+    m.Close()
+    assert rel_err(got_p, ref_p) <= TOL and rel_err(got_n, ref_n) <= TOL
+    assert same_values(got_p, ref_p)
+    assert same_values(got_n, ref_n)
+
+
+def test_ragged_instance_ranges_and_f64(oracle, gpu_ctx):
+    import zenyth_b200 as zn
+    counts = np.array([1, 2, 3, 1023, 1024, 1025, 5, 4000, 0, 17], np.uint32)
+    first = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+    V = int(first[-1])
+    pos, nrm = oracle.synth_mesh(BASE_SEED + 4, V)
+    models = models_from_scene(oracle, counts.size)
+    ref_p, ref_n = oracle.mesh_transform(first, models, pos, nrm)
+    m = zn.Mesh(gpu_ctx, V, counts.size, first)
+    m.SetVertices(pos, nrm)
+    m.SetModels(models)
+    m.Transform()
+    got_p, got_n = m.Read()
+    m.Close()
+    assert same_values(got_p, ref_p) and same_values(got_n, ref_n)
+    p64, n64 = oracle.mesh_transform64(first, models, pos, nrm)
+    assert rel_err(got_p, p64) <= TOL and rel_err(got_n, n64) <= TOL
+    assert np.allclose(np.linalg.norm(got_n.astype(np.float64), axis=1), 1.0, atol=1e-6)
+
+
+def test_models_bound_to_scene_world(oracle, gpu_ctx):
+    import zenyth_b200 as zn
+    I, verts = 16, 1024
+    arrays = oracle.synth_scene(BASE_SEED + 2, [I], fanout=1)
+    arrays["parent"] = None
+    arrays["level_offsets"] = None
+    view, proj = camera(oracle)
+    world = oracle.scene_update(arrays, view, proj)["world"]
+    sc = zn.Scene(gpu_ctx, I)
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    sc.Update()
+    m = zn.Mesh(gpu_ctx, I * verts, I)
+    m.FillSynthetic(BASE_SEED + 4)
+    pos, nrm = oracle.synth_mesh(BASE_SEED + 4, I * verts)
+    gp, gn = m.Inputs()
+    assert np.array_equal(gp.view(np.uint32), pos.view(np.uint32)) and np.array_equal(gn.view(np.uint32), nrm.view(np.uint32))
+    m.BindSceneModels(sc, 0)
+    m.Transform()
+    got_p, got_n = m.Read()
+    first = (np.arange(I + 1, dtype=np.uint32) * verts).astype(np.uint32)
+    ref_p, ref_n = oracle.mesh_transform(first, world, pos, nrm)
+    assert same_values(got_p, ref_p) and same_values(got_n, ref_n)
+    m.Close()
+    sc.Close()

@@ -1,0 +1,158 @@
+"""-m gpu: the CUDA scene path, through the C ABI, against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+from conftest import rel_err, same_values
+from oracle.binding import BASE_SEED, camera, h8_geo_level_sizes
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5   # north star: world/MVP within 1e-5 relative; the design target is exact equality
+
+
+def run_gpu(gpu_ctx, arrays, view, proj, index_base=0):
+    import zenyth_b200 as zn
+    sc = zn.Scene(gpu_ctx, arrays["position"].shape[0], arrays.get("level_offsets"))
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    if index_base:
+        sc.SetIndexBase(index_base)
+    sc.Update()
+    out = {"world": sc.World(), "mvp": sc.Mvp(), "visible": sc.Visible(), "count": sc.VisibleCount()}
+    sc.Close()
+    return out
+
+
+def check_against_oracle(oracle, gpu_ctx, arrays, view, proj, exact=True):
+    ref = oracle.scene_update(arrays, view, proj, threads=4)
+    got = run_gpu(gpu_ctx, arrays, view, proj)
+    assert rel_err(got["world"], ref["world"]) <= TOL
+    assert rel_err(got["mvp"], ref["mvp"]) <= TOL
+    if exact:
+        # same operation order on both sides: equal to the last bit (modulo the sign of zero)
+        assert same_values(got["world"], ref["world"])
+        assert same_values(got["mvp"], ref["mvp"])
+    assert got["count"] == ref["visible"].size
+    assert np.array_equal(got["visible"], ref["visible"])   # bit-exact, ascending
+    return ref, got
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 255, 256, 257, 1000, 4097])
+def test_flat_ragged_sizes(oracle, gpu_ctx, n):
+    arrays = oracle.synth_scene(BASE_SEED + 2, [n], fanout=1, center_range=0.5)
+    arrays["parent"] = None
+    arrays["level_offsets"] = None
+    view, proj = camera(oracle)
+    ref, _ = check_against_oracle(oracle, gpu_ctx, arrays, view, proj)
+
+
+def test_flat_64k_three_cameras(oracle, gpu_ctx):
+    arrays = oracle.synth_scene(BASE_SEED + 2, [65536], fanout=1, center_range=0.0)
+    fractions = []
+    for eye in [(0, 0, 0), (0, 0, 1500), (0, 0, 3000)]:
+        view, proj = camera(oracle, eye=eye)
+        ref, _ = check_against_oracle(oracle, gpu_ctx, arrays, view, proj)
+        fractions.append(ref["visible"].size / 65536)
+    assert fractions[0] < fractions[1] < fractions[2]
+
+
+def test_hierarchy_h8_geo_5_levels(oracle, gpu_ctx):
+    arrays = oracle.synth_scene(BASE_SEED + 3, h8_geo_level_sizes(7, 5), fanout=8, center_range=0.25)
+    view, proj = camera(oracle)
+    check_against_oracle(oracle, gpu_ctx, arrays, view, proj)
+
+
+def test_hierarchy_chain_fanout1(oracle, gpu_ctx):
+    arrays = oracle.synth_scene(BASE_SEED + 3, [3000] * 6, fanout=1, center_range=0.25)
+    view, proj = camera(oracle)
+    check_against_oracle(oracle, gpu_ctx, arrays, view, proj)
+
+
+def test_hierarchy_scattered_parents_take_the_gather_path(oracle, gpu_ctx):
+    # children are NOT sorted by parent: parent ranges per tile exceed the staging window
+    rng = np.random.default_rng(7)
+    sizes = [2000, 5000, 5000]
+    arrays = oracle.synth_scene(BASE_SEED + 4, sizes, fanout=2, center_range=0.25)
+    off = arrays["level_offsets"]
+    for l in range(1, 3):
+        arrays["parent"][off[l]:off[l + 1]] = rng.integers(off[l - 1], off[l], sizes[l], dtype=np.uint32)
+    # a few roots inside deeper levels
+    arrays["parent"][off[1] + 5] = 0xFFFFFFFF
+    arrays["parent"][off[2] + 77] = 0xFFFFFFFF
+    view, proj = camera(oracle)
+    check_against_oracle(oracle, gpu_ctx, arrays, view, proj)
+
+
+def test_matches_float64_shadow_outside_boundary_set(oracle, gpu_ctx):
+    arrays = oracle.synth_scene(BASE_SEED + 3, h8_geo_level_sizes(7, 5), fanout=8, center_range=0.25)
+    view, proj = camera(oracle)
+    got = run_gpu(gpu_ctx, arrays, view, proj)
+    d = oracle.scene_update64(arrays, view, proj, eps=1e-5)
+    assert rel_err(got["world"], d["world"]) <= TOL
+    assert rel_err(got["mvp"], d["mvp"]) <= TOL
+    flags = np.zeros(arrays["position"].shape[0], np.uint8)
+    flags[got["visible"]] = 1
+    mismatch = flags != d["visible"]
+    assert not np.any(mismatch & (d["boundary"] == 0))
+
+
+def test_index_base_and_rerun_idempotent(oracle, gpu_ctx):
+    import zenyth_b200 as zn
+    arrays = oracle.synth_scene(BASE_SEED + 5, [300, 2400], fanout=8)
+    view, proj = camera(oracle)
+    ref = oracle.scene_update(arrays, view, proj)
+    sc = zn.Scene(gpu_ctx, 2700, arrays["level_offsets"])
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    sc.SetIndexBase(1000)
+    sc.Update()
+    a = sc.Visible()
+    sc.Update()
+    b = sc.Visible()
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, ref["visible"] + 1000)
+    sc.Close()
+
+
+def test_vec3_stride16_upload(oracle, gpu_ctx):
+    import zenyth_b200 as zn
+    arrays = oracle.synth_scene(BASE_SEED + 6, [777], fanout=1)
+    view, proj = camera(oracle)
+    ref = oracle.scene_update(arrays, view, proj)
+    pad = lambda a: np.concatenate([a, np.full((a.shape[0], 1), 123.0, np.float32)], axis=1)
+    sc = zn.Scene(gpu_ctx, 777)
+    sc.SetTransforms(pad(arrays["position"]), pad(arrays["rotation"]), pad(arrays["scale"]))
+    sc.SetBounds(pad(arrays["aabb_center"]), pad(arrays["aabb_half"]))
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    sc.Update()
+    assert same_values(sc.World(), ref["world"])
+    assert np.array_equal(sc.Visible(), ref["visible"])
+    back = sc.Inputs()
+    assert np.array_equal(back["position"], arrays["position"])
+    assert np.array_equal(back["aabb_half"], arrays["aabb_half"])
+    sc.Close()
+
+
+def test_device_synth_matches_host_generator(oracle, gpu_ctx):
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 4)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    sc = zn.Scene(gpu_ctx, sum(sizes), arrays["level_offsets"])
+    sc.FillSynthetic(BASE_SEED + 3, 8, 0.25)
+    back = sc.Inputs()
+    for k in ("position", "rotation", "scale", "aabb_center", "aabb_half"):
+        assert np.array_equal(back[k].view(np.uint32), arrays[k].view(np.uint32)), k
+    assert np.array_equal(back["parent"], arrays["parent"])
+    sc.Close()
+
+
+def test_errors_are_loud(gpu_ctx):
+    import zenyth_b200 as zn
+    sc = zn.Scene(gpu_ctx, 16)
+    with pytest.raises(zn.ZenythError):
+        sc.Update()   # no camera
+    with pytest.raises(zn.ZenythError):
+        sc.SetParents(np.array([3], np.uint32), first=0)   # parent not in an earlier level
+    with pytest.raises(zn.ZenythError):
+        sc.World(first=10, count=10)
+    sc.Close()

@@ -1,0 +1,130 @@
+"""ctypes binding of include/zenyth_b200.h — one prototype per exported symbol.
+
+The library is the product; there is no Python or CPU fallback.  If libzenyth_b200.so is missing
+`load()` raises with the build command instead of degrading.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libzenyth_b200.so")
+
+ZN_OK = 0
+ZN_ERR_INVALID = 1
+ZN_ERR_CUDA = 2
+ZN_ERR_NO_DEVICE = 3
+ZN_ERR_STATE = 4
+ZN_ERR_NOMEM = 5
+ZN_NO_PARENT = 0xFFFFFFFF
+
+c_float_p = C.POINTER(C.c_float)
+c_u32_p = C.POINTER(C.c_uint32)
+vp = C.c_void_p
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("entity_count", C.c_uint32), ("level_count", C.c_uint32), ("level_offsets", vp)]
+
+
+class SceneBuffers(C.Structure):
+    _fields_ = [("world", vp), ("mvp", vp), ("visible", vp), ("visible_count", vp), ("entity_count", C.c_uint32)]
+
+
+class FrameHostIO(C.Structure):
+    _fields_ = [("position", vp), ("rotation", vp), ("scale", vp), ("world", vp), ("mvp", vp), ("visible", vp),
+                ("visible_count", C.c_uint32)]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("vertex_count", C.c_uint32), ("instance_count", C.c_uint32), ("instance_first_vertex", vp)]
+
+
+class MeshBuffers(C.Structure):
+    _fields_ = [("position_in", vp), ("normal_in", vp), ("position_out", vp), ("normal_out", vp), ("vertex_count", C.c_uint32)]
+
+
+# symbol -> (restype, argtypes).  tests/test_abi.py checks this table against include/zenyth_b200.h.
+PROTOTYPES = {
+    "zn_abi_version": (C.c_int, []),
+    "zn_last_error": (C.c_char_p, []),
+    "zn_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "zn_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "zn_ctx_destroy": (C.c_int, [vp]),
+    "zn_ctx_set_stream": (C.c_int, [vp, vp]),
+    "zn_ctx_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
+    "zn_ctx_sync": (C.c_int, [vp]),
+    "zn_ctx_sm_count": (C.c_int, [vp, C.POINTER(C.c_int)]),
+    "zn_host_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "zn_host_free": (C.c_int, [vp, vp]),
+    "zn_mat4_look_at": (None, [vp, vp, vp, vp]),
+    "zn_mat4_perspective": (None, [C.c_float, C.c_float, C.c_float, C.c_float, vp]),
+    "zn_mat4_orthographic": (None, [C.c_float] * 6 + [vp]),
+    "zn_mat4_perspective_reverse_z": (None, [C.c_float, C.c_float, C.c_float, vp]),
+    "zn_mat4_mul": (None, [vp, vp, vp]),
+    "zn_frustum_planes": (None, [vp, vp]),
+    "zn_scene_create": (C.c_int, [vp, C.POINTER(SceneDesc), C.POINTER(vp)]),
+    "zn_scene_destroy": (C.c_int, [vp]),
+    "zn_scene_set_transforms": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_size_t]),
+    "zn_scene_set_bounds": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_size_t]),
+    "zn_scene_set_parents": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
+    "zn_scene_set_camera": (C.c_int, [vp, vp, vp]),
+    "zn_scene_set_index_base": (C.c_int, [vp, C.c_uint32]),
+    "zn_scene_update": (C.c_int, [vp]),
+    "zn_scene_visible_count": (C.c_int, [vp, c_u32_p]),
+    "zn_scene_read_visible": (C.c_int, [vp, vp, C.c_uint32, c_u32_p]),
+    "zn_scene_read_world": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
+    "zn_scene_read_mvp": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
+    "zn_scene_read_inputs": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]),
+    "zn_scene_device_buffers": (C.c_int, [vp, C.POINTER(SceneBuffers)]),
+    "zn_scene_frame_host": (C.c_int, [vp, C.POINTER(FrameHostIO)]),
+    "zn_scene_algorithmic_bytes": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "zn_scene_launches_per_update": (C.c_int, [vp, c_u32_p]),
+    "zn_mesh_create": (C.c_int, [vp, C.POINTER(MeshDesc), C.POINTER(vp)]),
+    "zn_mesh_destroy": (C.c_int, [vp]),
+    "zn_mesh_set_vertices": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_size_t]),
+    "zn_mesh_set_models": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
+    "zn_mesh_bind_scene_models": (C.c_int, [vp, vp, C.c_uint32]),
+    "zn_mesh_transform": (C.c_int, [vp]),
+    "zn_mesh_read": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp]),
+    "zn_mesh_read_inputs": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp]),
+    "zn_mesh_device_buffers": (C.c_int, [vp, C.POINTER(MeshBuffers)]),
+    "zn_scene_fill_synthetic": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_float]),
+    "zn_mesh_fill_synthetic": (C.c_int, [vp, C.c_uint32]),
+}
+
+_lib = None
+
+
+class ZenythError(RuntimeError):
+    """Raised for any non-zero status, mirroring the reference's std::runtime_error convention
+    (Core/src/Application.cpp:28-30)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[zn error {code}] {message}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m zenyth_b200.build` (nvcc, sm_100a). "
+            "zenyth_b200 has no CPU or Python fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)   # AttributeError here = the .so does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.zn_abi_version() != 1:
+        raise ImportError(f"libzenyth_b200.so ABI version {lib.zn_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != ZN_OK:
+        raise ZenythError(code, load().zn_last_error().decode("utf-8", "replace"))

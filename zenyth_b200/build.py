@@ -1,0 +1,65 @@
+"""Build recipe for libzenyth_b200.so (the C-ABI CUDA library) — sm_100a only, in-tree.
+
+    python -m zenyth_b200.build [--verbose]
+
+The .so lands in zenyth_b200/lib/ (git-ignored, but it travels with the repo snapshot to the GPU
+box).  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB_DIR = os.path.join(PKG, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libzenyth_b200.so")
+SOURCES = ["zn_ctx.cu", "zn_scene.cu", "zn_mesh.cu", "zn_synth.cu", "zn_hostmath.cpp"]
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    # The kernels spell every float op as an explicit _rn intrinsic; -fmad=false is the belt to
+    # that pair of braces (no contraction anywhere in device code).
+    "-fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-shared",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG, "..", "include", "zenyth_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", LIB_PATH, *SOURCES]
+    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed building libzenyth_b200.so")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(verbose="--verbose" in sys.argv, force=True))

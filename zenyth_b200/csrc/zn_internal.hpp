@@ -1,0 +1,100 @@
+// zn_internal.hpp — host-side plumbing shared by the translation units of libzenyth_b200.so.
+#pragma once
+#include "../../include/zenyth_b200.h"
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace zn {
+
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define ZN_CUDA(expr)                                                                             \
+	do {                                                                                          \
+		cudaError_t zn_e_ = (expr);                                                               \
+		if (zn_e_ != cudaSuccess)                                                                 \
+			return ::zn::fail(ZN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(zn_e_), __FILE__, __LINE__); \
+	} while (0)
+
+#define ZN_REQUIRE(cond, ...)                                  \
+	do {                                                       \
+		if (!(cond)) return ::zn::fail(ZN_ERR_INVALID, __VA_ARGS__); \
+	} while (0)
+
+// Entities (or vertices /4) handled by one CTA.
+constexpr int kTile = 256;
+constexpr int kMeshTileVerts = 1024;
+
+// Builds a 2-D tensor map over a float[rows][16] matrix array: box {16, kTile}, 64-byte swizzle.
+int encode_matrix_tensor_map(CUtensorMap* out, void* base, uint64_t rows);
+
+} // namespace zn
+
+struct zn_ctx {
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t stream = nullptr;
+	void* staging = nullptr;       // device staging for strided uploads
+	size_t staging_bytes = 0;
+};
+
+struct zn_level {
+	uint32_t begin = 0, end = 0;   // entity range
+	uint32_t tile_base = 0;        // first global tile id of this level
+	uint32_t tiles = 0;
+	CUtensorMap tm_world, tm_mvp;  // extent clipped to `end` rows
+};
+
+struct zn_scene {
+	zn_ctx* ctx = nullptr;
+	uint32_t entity_count = 0;
+	std::vector<zn_level> levels;
+	uint32_t tile_count = 0;
+	uint32_t index_base = 0;
+	bool has_camera = false;
+	float view_proj[16];
+	float planes[24];
+	// inputs, SoA: 15 float arrays + parent
+	float* soa = nullptr;          // [15][E_padded]
+	size_t soa_pitch = 0;          // elements between component arrays
+	uint32_t* parent = nullptr;    // [E]
+	// outputs
+	float* world = nullptr;        // [E][16]
+	float* mvp = nullptr;          // [E][16]
+	uint32_t* visible = nullptr;   // [E]
+	uint32_t* visible_count = nullptr; // [1] device
+	uint32_t* tile_vis_count = nullptr;  // [tiles]
+	uint32_t* tile_vis_offset = nullptr; // [tiles]
+	uint32_t* tile_mask = nullptr;       // [tiles][kTile/32]
+	uint32_t* tile_first_entity = nullptr; // [tiles]
+	uint32_t* host_count = nullptr;      // pinned [1]
+};
+
+struct zn_mesh_tile {
+	uint32_t first_vertex;
+	uint32_t vertex_count;
+	uint32_t instance;
+	uint32_t flags;                // bit0: bulk (TMA) path eligible
+};
+
+struct zn_mesh {
+	zn_ctx* ctx = nullptr;
+	uint32_t vertex_count = 0;
+	uint32_t instance_count = 0;
+	uint32_t tile_count = 0;
+	zn_mesh_tile* tiles = nullptr;   // device [tile_count]
+	float* pos_in = nullptr;         // [V][3]
+	float* nrm_in = nullptr;
+	float* pos_out = nullptr;
+	float* nrm_out = nullptr;
+	float* models_own = nullptr;     // [I][16]
+	const float* models = nullptr;   // models_own or a scene's world array
+};

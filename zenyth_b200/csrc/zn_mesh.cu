@@ -1,0 +1,296 @@
+// zn_mesh.cu — K4: bulk mesh vertex / normal transform by per-instance model matrices.
+//
+//   pos' = model.transform_point(pos)                                   (matrix.hpp:45-46)
+//   nrm' = normalize(model.inverse_transpose().transform_normal(nrm))   (matrix.hpp:43,47-48)
+//
+// Vertices are packed float[V][3] streams (48 algorithmic bytes per vertex in + out).  A CTA owns
+// a tile of up to 1024 vertices of ONE instance: thread 0 pulls the tile's positions and normals
+// into shared memory with two cp.async.bulk copies (12 KiB each) while thread 32 inverts the
+// instance's model matrix; every thread then transforms 4 vertices in place (12-word stride:
+// conflict-free float4 shared accesses) and the tile leaves as two bulk stores.  No thread issues
+// a global load or store for vertex data on this path, and HBM only sees 12 KiB bursts.
+// Tiles whose range is not 4-vertex aligned take a cooperative LDG/STG path through the same
+// shared buffers.
+#include "zn_internal.hpp"
+#include "zn_math.cuh"
+#include "zn_ptx.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace zn {
+
+constexpr int kMeshThreads = kMeshTileVerts / 4;
+
+__global__ void __launch_bounds__(kMeshThreads, 4)
+mesh_tile_kernel(const zn_mesh_tile* __restrict__ tiles, const float* __restrict__ models,
+                 const float* __restrict__ pos_in, const float* __restrict__ nrm_in,
+                 float* __restrict__ pos_out, float* __restrict__ nrm_out) {
+	__shared__ __align__(128) float s_pos[kMeshTileVerts * 3];
+	__shared__ __align__(128) float s_nrm[kMeshTileVerts * 3];
+	__shared__ float s_model[12];   // rows 0..2 of the model, row-major [r*4+c]
+	__shared__ float s_nm[9];       // upper 3x3 of (model^-1)^T, row-major
+	__shared__ uint64_t s_bar;
+
+	const int t = threadIdx.x;
+	const zn_mesh_tile tile = tiles[blockIdx.x];
+	const bool bulk = (tile.flags & 1u) != 0;
+	const uint32_t floats = tile.vertex_count * 3;
+	const size_t base = size_t(tile.first_vertex) * 3;
+
+	if (t == 0) {
+		mbar_init(&s_bar, 1);
+		fence_mbar_init();
+		if (bulk) {
+			mbar_arrive_expect_tx(&s_bar, floats * 8);
+			bulk_g2s(s_pos, pos_in + base, floats * 4, &s_bar);
+			bulk_g2s(s_nrm, nrm_in + base, floats * 4, &s_bar);
+		}
+	} else if (t == 32) {
+		float m[16], inv[16];
+		const float4* src = reinterpret_cast<const float4*>(models + size_t(tile.instance) * 16);
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			const float4 col = __ldg(src + c);
+			m[c * 4 + 0] = col.x; m[c * 4 + 1] = col.y; m[c * 4 + 2] = col.z; m[c * 4 + 3] = col.w;
+		}
+		mat4_inverse(m, inv);
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+#pragma unroll
+			for (int c = 0; c < 4; ++c) s_model[r * 4 + c] = m[c * 4 + r];
+#pragma unroll
+			for (int c = 0; c < 3; ++c) s_nm[r * 3 + c] = inv[r * 4 + c];   // transpose(inverse)(r,c) = inverse(c,r)
+		}
+	}
+	if (!bulk) {
+		for (uint32_t k = t; k < floats; k += kMeshThreads) {
+			s_pos[k] = ld_stream(pos_in + base + k);
+			s_nrm[k] = ld_stream(nrm_in + base + k);
+		}
+	}
+	__syncthreads();
+	if (bulk) mbar_wait(&s_bar, 0);
+
+	if (uint32_t(t) * 4 < tile.vertex_count) {
+		float M[12], N[9];
+#pragma unroll
+		for (int k = 0; k < 12; ++k) M[k] = s_model[k];
+#pragma unroll
+		for (int k = 0; k < 9; ++k) N[k] = s_nm[k];
+		float4* pp = reinterpret_cast<float4*>(s_pos) + t * 3;
+		float4* np = reinterpret_cast<float4*>(s_nrm) + t * 3;
+		float4 a = pp[0], b = pp[1], c = pp[2];
+		float p[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+		a = np[0]; b = np[1]; c = np[2];
+		float n[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+		for (int v = 0; v < 4; ++v) {
+			const float px = p[3 * v], py = p[3 * v + 1], pz = p[3 * v + 2];
+			const float nx = n[3 * v], ny = n[3 * v + 1], nz = n[3 * v + 2];
+			float q[3], g[3];
+#pragma unroll
+			for (int r = 0; r < 3; ++r) {
+				q[r] = add(add(add(mul(M[r * 4 + 0], px), mul(M[r * 4 + 1], py)), mul(M[r * 4 + 2], pz)), M[r * 4 + 3]);
+				g[r] = add(add(mul(N[r * 3 + 0], nx), mul(N[r * 3 + 1], ny)), mul(N[r * 3 + 2], nz));
+			}
+			const float len = __fsqrt_rn(add(add(mul(g[0], g[0]), mul(g[1], g[1])), mul(g[2], g[2])));
+			if (len > 0.0f) { g[0] = __fdiv_rn(g[0], len); g[1] = __fdiv_rn(g[1], len); g[2] = __fdiv_rn(g[2], len); }
+			p[3 * v] = q[0]; p[3 * v + 1] = q[1]; p[3 * v + 2] = q[2];
+			n[3 * v] = g[0]; n[3 * v + 1] = g[1]; n[3 * v + 2] = g[2];
+		}
+		pp[0] = make_float4(p[0], p[1], p[2], p[3]); pp[1] = make_float4(p[4], p[5], p[6], p[7]); pp[2] = make_float4(p[8], p[9], p[10], p[11]);
+		np[0] = make_float4(n[0], n[1], n[2], n[3]); np[1] = make_float4(n[4], n[5], n[6], n[7]); np[2] = make_float4(n[8], n[9], n[10], n[11]);
+	}
+	if (bulk) {
+		fence_proxy_async_smem();
+		__syncthreads();
+		if (t == 0) {
+			bulk_s2g(pos_out + base, s_pos, floats * 4);
+			bulk_s2g(nrm_out + base, s_nrm, floats * 4);
+			bulk_commit();
+			bulk_wait_read_all();
+		}
+	} else {
+		__syncthreads();
+		for (uint32_t k = t; k < floats; k += kMeshThreads) {
+			pos_out[base + k] = s_pos[k];
+			nrm_out[base + k] = s_nrm[k];
+		}
+	}
+}
+
+// strided 3-float host records -> packed float[count][3]
+__global__ void pack3_kernel(const float* __restrict__ src, uint32_t stride_f, uint32_t count, float* __restrict__ dst) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const float* s = src + size_t(i) * stride_f;
+	dst[size_t(i) * 3 + 0] = s[0]; dst[size_t(i) * 3 + 1] = s[1]; dst[size_t(i) * 3 + 2] = s[2];
+}
+
+static int upload_vertices(zn_mesh* m, float* dst, uint32_t first, uint32_t count, const float* host, size_t stride_bytes) {
+	if (!host || count == 0) return ZN_OK;
+	zn_ctx* ctx = m->ctx;
+	if (stride_bytes == 12) {
+		ZN_CUDA(cudaMemcpyAsync(dst + size_t(first) * 3, host, size_t(count) * 12, cudaMemcpyHostToDevice, ctx->stream));
+		return ZN_OK;
+	}
+	const uint32_t chunk = 1u << 22;
+	const size_t need = size_t(std::min(count, chunk)) * stride_bytes;
+	if (ctx->staging_bytes < need) {
+		ZN_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (ctx->staging) ZN_CUDA(cudaFree(ctx->staging));
+		ctx->staging = nullptr; ctx->staging_bytes = 0;
+		ZN_CUDA(cudaMalloc(&ctx->staging, need));
+		ctx->staging_bytes = need;
+	}
+	for (uint32_t done = 0; done < count; done += chunk) {
+		const uint32_t n = std::min(chunk, count - done);
+		ZN_CUDA(cudaMemcpyAsync(ctx->staging, reinterpret_cast<const uint8_t*>(host) + size_t(done) * stride_bytes,
+		                        size_t(n - 1) * stride_bytes + 12, cudaMemcpyHostToDevice, ctx->stream));
+		pack3_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->staging), uint32_t(stride_bytes / 4), n,
+		                                                      dst + size_t(first + done) * 3);
+		ZN_CUDA(cudaGetLastError());
+	}
+	return ZN_OK;
+}
+
+} // namespace zn
+
+using namespace zn;
+
+extern "C" {
+
+int zn_mesh_create(zn_ctx* ctx, const zn_mesh_desc* desc, zn_mesh** out_mesh) {
+	ZN_REQUIRE(ctx && desc && out_mesh, "zn_mesh_create: NULL argument");
+	*out_mesh = nullptr;
+	const uint32_t V = desc->vertex_count, I = desc->instance_count;
+	ZN_REQUIRE(V > 0 && I > 0 && I <= V, "zn_mesh_create: need 0 < instance_count <= vertex_count (got %u, %u)", I, V);
+	ZN_REQUIRE(V <= 0x50000000u, "zn_mesh_create: vertex_count %u too large", V);
+	std::vector<uint32_t> first(size_t(I) + 1);
+	if (desc->instance_first_vertex) {
+		first.assign(desc->instance_first_vertex, desc->instance_first_vertex + I + 1);
+		ZN_REQUIRE(first.front() == 0 && first.back() == V, "zn_mesh_create: instance_first_vertex must start at 0 and end at vertex_count");
+		for (uint32_t k = 0; k < I; ++k) ZN_REQUIRE(first[k] <= first[k + 1], "zn_mesh_create: instance_first_vertex is not ascending at %u", k);
+	} else {
+		ZN_REQUIRE(V % I == 0, "zn_mesh_create: vertex_count %u is not a multiple of instance_count %u", V, I);
+		for (uint32_t k = 0; k <= I; ++k) first[k] = uint32_t(uint64_t(V / I) * k);
+	}
+	std::vector<zn_mesh_tile> tiles;
+	for (uint32_t k = 0; k < I; ++k)
+		for (uint32_t v = first[k]; v < first[k + 1]; v += kMeshTileVerts) {
+			zn_mesh_tile t;
+			t.first_vertex = v;
+			t.vertex_count = std::min<uint32_t>(kMeshTileVerts, first[k + 1] - v);
+			t.instance = k;
+			t.flags = (v % 4 == 0 && t.vertex_count % 4 == 0) ? 1u : 0u;
+			tiles.push_back(t);
+		}
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	zn_mesh* m = new zn_mesh();
+	m->ctx = ctx;
+	m->vertex_count = V;
+	m->instance_count = I;
+	m->tile_count = uint32_t(tiles.size());
+	auto cleanup = [&](int rc) { zn_mesh_destroy(m); return rc; };
+#define ZN_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return cleanup(fail(e_ == cudaErrorMemoryAllocation ? ZN_ERR_NOMEM : ZN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_))); } while (0)
+	ZN_TRY(cudaMalloc(&m->tiles, tiles.size() * sizeof(zn_mesh_tile)));
+	ZN_TRY(cudaMalloc(&m->pos_in, size_t(V) * 12));
+	ZN_TRY(cudaMalloc(&m->nrm_in, size_t(V) * 12));
+	ZN_TRY(cudaMalloc(&m->pos_out, size_t(V) * 12));
+	ZN_TRY(cudaMalloc(&m->nrm_out, size_t(V) * 12));
+	ZN_TRY(cudaMalloc(&m->models_own, size_t(I) * 64));
+	ZN_TRY(cudaMemcpyAsync(m->tiles, tiles.data(), tiles.size() * sizeof(zn_mesh_tile), cudaMemcpyHostToDevice, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(m->models_own, 0, size_t(I) * 64, ctx->stream));
+	ZN_TRY(cudaStreamSynchronize(ctx->stream));
+#undef ZN_TRY
+	m->models = m->models_own;
+	*out_mesh = m;
+	return ZN_OK;
+}
+
+int zn_mesh_destroy(zn_mesh* m) {
+	if (!m) return ZN_OK;
+	cudaSetDevice(m->ctx->device);
+	cudaStreamSynchronize(m->ctx->stream);
+	cudaFree(m->tiles); cudaFree(m->pos_in); cudaFree(m->nrm_in); cudaFree(m->pos_out); cudaFree(m->nrm_out); cudaFree(m->models_own);
+	delete m;
+	return ZN_OK;
+}
+
+int zn_mesh_set_vertices(zn_mesh* m, uint32_t first, uint32_t count, const float* position, const float* normal, size_t stride_bytes) {
+	ZN_REQUIRE(m, "zn_mesh_set_vertices: mesh is NULL");
+	ZN_REQUIRE(uint64_t(first) + count <= m->vertex_count, "zn_mesh_set_vertices: range exceeds vertex_count %u", m->vertex_count);
+	ZN_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "zn_mesh_set_vertices: stride_bytes %zu must be >= 12 and a multiple of 4", stride_bytes);
+	ZN_CUDA(cudaSetDevice(m->ctx->device));
+	int rc = upload_vertices(m, m->pos_in, first, count, position, stride_bytes);
+	if (rc == ZN_OK) rc = upload_vertices(m, m->nrm_in, first, count, normal, stride_bytes);
+	if (rc != ZN_OK) return rc;
+	ZN_CUDA(cudaStreamSynchronize(m->ctx->stream));
+	return ZN_OK;
+}
+
+int zn_mesh_set_models(zn_mesh* m, uint32_t first, uint32_t count, const float* model_matrices) {
+	ZN_REQUIRE(m && (model_matrices || count == 0), "zn_mesh_set_models: NULL argument");
+	ZN_REQUIRE(uint64_t(first) + count <= m->instance_count, "zn_mesh_set_models: range exceeds instance_count %u", m->instance_count);
+	ZN_CUDA(cudaSetDevice(m->ctx->device));
+	ZN_CUDA(cudaMemcpyAsync(m->models_own + size_t(first) * 16, model_matrices, size_t(count) * 64, cudaMemcpyHostToDevice, m->ctx->stream));
+	ZN_CUDA(cudaStreamSynchronize(m->ctx->stream));
+	m->models = m->models_own;
+	return ZN_OK;
+}
+
+int zn_mesh_bind_scene_models(zn_mesh* m, zn_scene* scene, uint32_t first_entity) {
+	ZN_REQUIRE(m && scene, "zn_mesh_bind_scene_models: NULL argument");
+	ZN_REQUIRE(m->ctx == scene->ctx, "zn_mesh_bind_scene_models: mesh and scene belong to different contexts");
+	ZN_REQUIRE(uint64_t(first_entity) + m->instance_count <= scene->entity_count,
+	           "zn_mesh_bind_scene_models: entities [%u, %u+%u) exceed the scene's %u", first_entity, first_entity, m->instance_count, scene->entity_count);
+	m->models = scene->world + size_t(first_entity) * 16;
+	return ZN_OK;
+}
+
+int zn_mesh_transform(zn_mesh* m) {
+	ZN_REQUIRE(m, "zn_mesh_transform: mesh is NULL");
+	ZN_CUDA(cudaSetDevice(m->ctx->device));
+	mesh_tile_kernel<<<m->tile_count, kMeshThreads, 0, m->ctx->stream>>>(m->tiles, m->models, m->pos_in, m->nrm_in, m->pos_out, m->nrm_out);
+	ZN_CUDA(cudaGetLastError());
+	return ZN_OK;
+}
+
+static int read_packed(zn_mesh* m, const float* dev, uint32_t first, uint32_t count, float* out) {
+	if (!out || count == 0) return ZN_OK;
+	ZN_CUDA(cudaMemcpyAsync(out, dev + size_t(first) * 3, size_t(count) * 12, cudaMemcpyDeviceToHost, m->ctx->stream));
+	return ZN_OK;
+}
+
+int zn_mesh_read(zn_mesh* m, uint32_t first, uint32_t count, float* out_position, float* out_normal) {
+	ZN_REQUIRE(m, "zn_mesh_read: mesh is NULL");
+	ZN_REQUIRE(uint64_t(first) + count <= m->vertex_count, "zn_mesh_read: range exceeds vertex_count %u", m->vertex_count);
+	ZN_CUDA(cudaSetDevice(m->ctx->device));
+	int rc = read_packed(m, m->pos_out, first, count, out_position);
+	if (rc == ZN_OK) rc = read_packed(m, m->nrm_out, first, count, out_normal);
+	if (rc != ZN_OK) return rc;
+	ZN_CUDA(cudaStreamSynchronize(m->ctx->stream));
+	return ZN_OK;
+}
+
+int zn_mesh_read_inputs(zn_mesh* m, uint32_t first, uint32_t count, float* position, float* normal) {
+	ZN_REQUIRE(m, "zn_mesh_read_inputs: mesh is NULL");
+	ZN_REQUIRE(uint64_t(first) + count <= m->vertex_count, "zn_mesh_read_inputs: range exceeds vertex_count %u", m->vertex_count);
+	ZN_CUDA(cudaSetDevice(m->ctx->device));
+	int rc = read_packed(m, m->pos_in, first, count, position);
+	if (rc == ZN_OK) rc = read_packed(m, m->nrm_in, first, count, normal);
+	if (rc != ZN_OK) return rc;
+	ZN_CUDA(cudaStreamSynchronize(m->ctx->stream));
+	return ZN_OK;
+}
+
+int zn_mesh_device_buffers(zn_mesh* m, zn_mesh_buffers* out) {
+	ZN_REQUIRE(m && out, "zn_mesh_device_buffers: NULL argument");
+	out->position_in = m->pos_in; out->normal_in = m->nrm_in;
+	out->position_out = m->pos_out; out->normal_out = m->nrm_out;
+	out->vertex_count = m->vertex_count;
+	return ZN_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,368 @@
+"""Host-side mirror of the engine-idiom API (include/zenyth_b200.hpp) over the C ABI.
+
+Class and method names follow the reference's engine layer (namespace Zenyth, PascalCase methods,
+Desc aggregates — Core/include/Application.hpp:9-14,26-40); the maths keeps the reference's
+snake_case (Core/include/math/matrix.hpp:19-55).  Everything here is plumbing: numpy arrays in,
+ctypes calls to libzenyth_b200.so, numpy arrays out.  No arithmetic of the path happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+from ._capi import ZN_NO_PARENT, ZenythError, check
+
+__all__ = ["GpuContext", "Transform", "CameraDesc", "Camera", "Scene", "Mesh", "mat4", "ZN_NO_PARENT", "ZenythError"]
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class mat4:
+    """The camera-side completion of zenyth::math::mat4 (static factories, matrix.hpp:32,52-55).
+    Matrices are float32[16], column-major, as mat4::data()."""
+
+    @staticmethod
+    def look_at(eye, center, up) -> np.ndarray:
+        out = np.zeros(16, np.float32)
+        _capi.load().zn_mat4_look_at(_p(_f32(eye, 3)), _p(_f32(center, 3)), _p(_f32(up, 3)), _p(out))
+        return out
+
+    @staticmethod
+    def perspective(fov_y: float, aspect: float, near_z: float, far_z: float) -> np.ndarray:
+        out = np.zeros(16, np.float32)
+        _capi.load().zn_mat4_perspective(fov_y, aspect, near_z, far_z, _p(out))
+        return out
+
+    @staticmethod
+    def orthographic(left, right, bottom, top, near_z, far_z) -> np.ndarray:
+        out = np.zeros(16, np.float32)
+        _capi.load().zn_mat4_orthographic(left, right, bottom, top, near_z, far_z, _p(out))
+        return out
+
+    @staticmethod
+    def perspective_reverse_z(fov_y: float, aspect: float, near_z: float) -> np.ndarray:
+        out = np.zeros(16, np.float32)
+        _capi.load().zn_mat4_perspective_reverse_z(fov_y, aspect, near_z, _p(out))
+        return out
+
+    @staticmethod
+    def mul(a, b) -> np.ndarray:
+        out = np.zeros(16, np.float32)
+        _capi.load().zn_mat4_mul(_p(_f32(a, 16)), _p(_f32(b, 16)), _p(out))
+        return out
+
+    @staticmethod
+    def frustum_planes(view_proj) -> np.ndarray:
+        out = np.zeros(24, np.float32)
+        _capi.load().zn_frustum_planes(_p(_f32(view_proj, 16)), _p(out))
+        return out.reshape(6, 4)
+
+
+class GpuContext:
+    """One per GPU (zn_ctx).  Move-only in the C++ wrapper; here: explicit Close() or context manager."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _capi.load()
+        h = C.c_void_p()
+        check(self._lib.zn_ctx_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        if stream is not None:
+            self.SetStream(stream)
+
+    def SetStream(self, cuda_stream: int | None) -> None:
+        check(self._lib.zn_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def Sync(self) -> None:
+        check(self._lib.zn_ctx_sync(self._h))
+
+    def SmCount(self) -> int:
+        n = C.c_int()
+        check(self._lib.zn_ctx_sm_count(self._h, C.byref(n)))
+        return n.value
+
+    def HostAlloc(self, shape, dtype) -> np.ndarray:
+        """Page-locked numpy array (freed with the context)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = C.c_void_p()
+        check(self._lib.zn_host_alloc(self._h, n, C.byref(ptr)))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def Close(self) -> None:
+        if getattr(self, "_h", None):
+            for ptr in getattr(self, "_pinned", []):
+                self._lib.zn_host_free(self._h, ptr)
+            self._pinned = []
+            self._lib.zn_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.Close()
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass
+
+
+@dataclass
+class Transform:
+    """Local TRS of one entity.  rotation = (pitch, yaw, roll) radians, as mat4::from_euler."""
+    position: tuple = (0.0, 0.0, 0.0)
+    rotation: tuple = (0.0, 0.0, 0.0)
+    scale: tuple = (1.0, 1.0, 1.0)
+
+
+@dataclass
+class CameraDesc:
+    eye: tuple = (0.0, 0.0, 0.0)
+    center: tuple = (0.0, 0.0, -1.0)
+    up: tuple = (0.0, 1.0, 0.0)
+    fov_y_rad: float = float(np.float32(60.0) * np.float32(np.pi) / np.float32(180.0))
+    aspect: float = 1280.0 / 720.0   # Sandbox/include/SandboxApp.hpp:6
+    near_z: float = 0.1
+    far_z: float = 5000.0
+
+
+class Camera:
+    def __init__(self, desc: CameraDesc | None = None, view=None, proj=None):
+        desc = desc or CameraDesc()
+        self.desc = desc
+        self.view = _f32(view, 16) if view is not None else mat4.look_at(desc.eye, desc.center, desc.up)
+        self.proj = _f32(proj, 16) if proj is not None else mat4.perspective(desc.fov_y_rad, desc.aspect, desc.near_z, desc.far_z)
+
+    def ViewProj(self) -> np.ndarray:
+        return mat4.mul(self.proj, self.view)
+
+    def Resize(self, width: int, height: int) -> None:
+        """What IRenderer::Resize (Core/include/IRenderer.hpp:11) feeds: a new aspect ratio."""
+        self.desc.aspect = float(width) / float(height)
+        self.proj = mat4.perspective(self.desc.fov_y_rad, self.desc.aspect, self.desc.near_z, self.desc.far_z)
+
+
+class Scene:
+    """Level-ordered entity hierarchy resident on one GPU (zn_scene)."""
+
+    def __init__(self, ctx: GpuContext, entity_count: int, level_offsets=None):
+        self._lib = _capi.load()
+        self.ctx = ctx
+        self.entity_count = int(entity_count)
+        lo = None if level_offsets is None else np.ascontiguousarray(level_offsets, np.uint32)
+        self.level_offsets = lo
+        desc = _capi.SceneDesc(self.entity_count, 0 if lo is None else lo.size - 1, _p(lo))
+        h = C.c_void_p()
+        check(self._lib.zn_scene_create(ctx._h, C.byref(desc), C.byref(h)))
+        self._h = h
+
+    # -- uploads ------------------------------------------------------------------------------
+    @staticmethod
+    def _records(a, count):
+        """Accept [count,3] packed or [count,4] (16-byte vec3) float32 arrays."""
+        if a is None:
+            return None, 0
+        a = np.ascontiguousarray(a, np.float32)
+        assert a.ndim == 2 and a.shape[0] == count and a.shape[1] in (3, 4), a.shape
+        return a, a.shape[1] * 4
+
+    def SetTransforms(self, position=None, rotation=None, scale=None, first: int = 0, count: int | None = None) -> None:
+        count = self._count(count, position, rotation, scale)
+        arrs = [self._records(a, count) for a in (position, rotation, scale)]
+        strides = {s for _, s in arrs if s}
+        assert len(strides) <= 1, "position/rotation/scale must share one stride"
+        stride = strides.pop() if strides else 12
+        check(self._lib.zn_scene_set_transforms(self._h, first, count, _p(arrs[0][0]), _p(arrs[1][0]), _p(arrs[2][0]), stride))
+
+    def SetTransform(self, index: int, t: Transform) -> None:
+        self.SetTransforms(np.asarray([t.position], np.float32), np.asarray([t.rotation], np.float32),
+                           np.asarray([t.scale], np.float32), first=index, count=1)
+
+    def SetBounds(self, aabb_center=None, aabb_half=None, first: int = 0, count: int | None = None) -> None:
+        count = self._count(count, aabb_center, aabb_half)
+        arrs = [self._records(a, count) for a in (aabb_center, aabb_half)]
+        strides = {s for _, s in arrs if s}
+        stride = strides.pop() if strides else 12
+        check(self._lib.zn_scene_set_bounds(self._h, first, count, _p(arrs[0][0]), _p(arrs[1][0]), stride))
+
+    def SetParents(self, parent, first: int = 0) -> None:
+        parent = np.ascontiguousarray(parent, np.uint32)
+        check(self._lib.zn_scene_set_parents(self._h, first, parent.size, _p(parent)))
+
+    def SetCamera(self, camera: Camera) -> None:
+        check(self._lib.zn_scene_set_camera(self._h, _p(camera.view), _p(camera.proj)))
+
+    def SetIndexBase(self, base: int) -> None:
+        check(self._lib.zn_scene_set_index_base(self._h, base))
+
+    def Load(self, arrays: dict) -> None:
+        """arrays: position/rotation/scale/aabb_center/aabb_half [E,3], parent [E] (optional)."""
+        self.SetTransforms(arrays["position"], arrays["rotation"], arrays["scale"])
+        self.SetBounds(arrays["aabb_center"], arrays["aabb_half"])
+        if arrays.get("parent") is not None:
+            self.SetParents(arrays["parent"])
+
+    def FillSynthetic(self, seed: int, fanout: int = 8, aabb_center_range: float = 0.0) -> None:
+        check(self._lib.zn_scene_fill_synthetic(self._h, seed & 0xFFFFFFFF, fanout, aabb_center_range))
+
+    def _count(self, count, *arrs):
+        if count is not None:
+            return int(count)
+        for a in arrs:
+            if a is not None:
+                return int(np.asarray(a).shape[0])
+        return 0
+
+    # -- frame --------------------------------------------------------------------------------
+    def Update(self) -> None:
+        """One frame, asynchronous: world, MVP, visible list (zn_scene_update)."""
+        check(self._lib.zn_scene_update(self._h))
+
+    def FrameHost(self, position=None, rotation=None, scale=None, world=None, mvp=None, visible=None) -> int:
+        """End-to-end frame with host buffers (zn_scene_frame_host). Returns the visible count."""
+        io = _capi.FrameHostIO(_p(position), _p(rotation), _p(scale), _p(world), _p(mvp), _p(visible), 0)
+        check(self._lib.zn_scene_frame_host(self._h, C.byref(io)))
+        return int(io.visible_count)
+
+    # -- results ------------------------------------------------------------------------------
+    def VisibleCount(self) -> int:
+        n = C.c_uint32()
+        check(self._lib.zn_scene_visible_count(self._h, C.byref(n)))
+        return n.value
+
+    def Visible(self) -> np.ndarray:
+        n = self.VisibleCount()
+        out = np.empty(n, np.uint32)
+        got = C.c_uint32()
+        check(self._lib.zn_scene_read_visible(self._h, _p(out), n, C.byref(got)))
+        return out[: got.value]
+
+    def World(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.entity_count - first if count is None else count
+        out = np.empty((count, 16), np.float32)
+        check(self._lib.zn_scene_read_world(self._h, first, count, _p(out)))
+        return out
+
+    def Mvp(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.entity_count - first if count is None else count
+        out = np.empty((count, 16), np.float32)
+        check(self._lib.zn_scene_read_mvp(self._h, first, count, _p(out)))
+        return out
+
+    def Inputs(self, first: int = 0, count: int | None = None) -> dict:
+        count = self.entity_count - first if count is None else count
+        out = {k: np.empty((count, 3), np.float32) for k in ("position", "rotation", "scale", "aabb_center", "aabb_half")}
+        out["parent"] = np.empty(count, np.uint32)
+        check(self._lib.zn_scene_read_inputs(self._h, first, count, _p(out["position"]), _p(out["rotation"]), _p(out["scale"]),
+                                             _p(out["aabb_center"]), _p(out["aabb_half"]), _p(out["parent"])))
+        return out
+
+    def DeviceBuffers(self) -> _capi.SceneBuffers:
+        b = _capi.SceneBuffers()
+        check(self._lib.zn_scene_device_buffers(self._h, C.byref(b)))
+        return b
+
+    def AlgorithmicBytes(self, visible_count: int) -> int:
+        n = C.c_uint64()
+        check(self._lib.zn_scene_algorithmic_bytes(self._h, visible_count, C.byref(n)))
+        return n.value
+
+    def LaunchesPerUpdate(self) -> int:
+        n = C.c_uint32()
+        check(self._lib.zn_scene_launches_per_update(self._h, C.byref(n)))
+        return n.value
+
+    def Close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.zn_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass
+
+
+class Mesh:
+    """A batch of instanced vertices (zn_mesh): positions + normals transformed per instance."""
+
+    def __init__(self, ctx: GpuContext, vertex_count: int, instance_count: int, instance_first_vertex=None):
+        self._lib = _capi.load()
+        self.ctx = ctx
+        self.vertex_count = int(vertex_count)
+        self.instance_count = int(instance_count)
+        fv = None if instance_first_vertex is None else np.ascontiguousarray(instance_first_vertex, np.uint32)
+        desc = _capi.MeshDesc(self.vertex_count, self.instance_count, _p(fv))
+        h = C.c_void_p()
+        check(self._lib.zn_mesh_create(ctx._h, C.byref(desc), C.byref(h)))
+        self._h = h
+
+    def SetVertices(self, position=None, normal=None, first: int = 0) -> None:
+        count = int((position if position is not None else normal).shape[0])
+        p, sp = Scene._records(position, count)
+        n, sn = Scene._records(normal, count)
+        stride = sp or sn or 12
+        check(self._lib.zn_mesh_set_vertices(self._h, first, count, _p(p), _p(n), stride))
+
+    def SetModels(self, models, first: int = 0) -> None:
+        models = _f32(models).reshape(-1, 16)
+        check(self._lib.zn_mesh_set_models(self._h, first, models.shape[0], _p(models)))
+
+    def BindSceneModels(self, scene: Scene, first_entity: int = 0) -> None:
+        check(self._lib.zn_mesh_bind_scene_models(self._h, scene._h, first_entity))
+        self._scene = scene   # keep alive
+
+    def FillSynthetic(self, seed: int) -> None:
+        check(self._lib.zn_mesh_fill_synthetic(self._h, seed & 0xFFFFFFFF))
+
+    def Transform(self) -> None:
+        check(self._lib.zn_mesh_transform(self._h))
+
+    def Read(self, first: int = 0, count: int | None = None):
+        count = self.vertex_count - first if count is None else count
+        pos = np.empty((count, 3), np.float32)
+        nrm = np.empty((count, 3), np.float32)
+        check(self._lib.zn_mesh_read(self._h, first, count, _p(pos), _p(nrm)))
+        return pos, nrm
+
+    def Inputs(self, first: int = 0, count: int | None = None):
+        count = self.vertex_count - first if count is None else count
+        pos = np.empty((count, 3), np.float32)
+        nrm = np.empty((count, 3), np.float32)
+        check(self._lib.zn_mesh_read_inputs(self._h, first, count, _p(pos), _p(nrm)))
+        return pos, nrm
+
+    def DeviceBuffers(self) -> _capi.MeshBuffers:
+        b = _capi.MeshBuffers()
+        check(self._lib.zn_mesh_device_buffers(self._h, C.byref(b)))
+        return b
+
+    def Close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.zn_mesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass
