@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — the headline measurement: TRS->world + MVP + frustum cull + compaction, M entities/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workload (BASELINE.json configs[2], the one the north-star target is quoted on): one synthetic
+"H8-geo" scene per GPU — 7 roots, fan-out 8, 8 levels, 16,777,215 entities, level-ordered — seen by
+the 'mid' camera of SURVEY.md §8(d).  A step is one zn_scene_update over that scene.  Inputs
+(1.07 GB) and outputs (2.15 GB) are far larger than the 126 MB L2, so no flush is needed between
+steps.  With N > 1 (torchrun, one rank per GPU) every rank owns one such scene (weak scaling) and
+the step also all-gathers the visible counts and the compacted index lists over NCCL.
+
+The JSON line carries, beside the driver contract: `roofline` (the dominant kernel — the last
+hierarchy level — timed with CUDA events inside the library, against MEASURED_PEAKS.json),
+`cpu_baseline` (the CPU oracle on the host cores, reported, not a target) and `e2e` (the same
+metric through zn_scene_frame_host with pinned HOST buffers: per step H2D of position/rotation/
+scale, D2H of the visible count + list).
+
+`--impl reference` times the CPU statement of the path (oracle/, on the reference's own vec3/vec4
+types when oracle/_ref is present) with all host threads.  The upstream engine has no
+implementation of this path to run, so the oracle IS the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASE_SEED = 0x5A454E59
+METRIC = "entities_per_second_trs_world_mvp_cull"
+UNIT = "M entities/s"
+
+WORKLOADS = {
+    # name: (roots, levels, fanout, description)
+    "h8geo16m": (7, 8, 8, "H8-geo: 7 roots, fan-out 8, 8 levels, 16,777,215 entities (BASELINE configs[2])"),
+    "flat1m": (1048576, 1, 1, "flat: 1,048,576 root entities (BASELINE configs[1])"),
+    "h8geo32m": (14, 8, 8, "H8-geo: 14 roots, fan-out 8, 8 levels, 33,554,430 entities (one scene of BASELINE configs[4])"),
+    "h8chain16m": (2097152, 8, 1, "H8-chain: 8 levels x 2,097,152, fan-out 1 (SURVEY §8d stress variant)"),
+}
+CAMERA_EYE = (0.0, 0.0, 1500.0)
+
+
+def level_sizes(roots, levels, fanout):
+    return [roots * fanout ** l for l in range(levels)]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: nvidia-smi sampled DURING the timed region
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id: str):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", gpu_id, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle, all host threads, preallocated buffers (first-touch done in warm-up)
+class CpuScene:
+    def __init__(self, workload: str, seed: int, reference_types: bool = False):
+        from oracle.binding import Oracle, _ptr, camera
+        self._ptr = _ptr
+        self.oracle = Oracle(reference_types=reference_types)
+        self.kind_note = ("oracle built on the reference's own zenyth::math vec3/vec4/mat4 (oracle/_ref; out-of-line SSE calls)"
+                          if reference_types else
+                          "oracle with the restated, inlined vec3/vec4/mat4 (the faster of the two oracle builds; "
+                          "bit-identical results to the oracle/_ref build on the reference's own types)")
+        roots, levels, fanout, _ = WORKLOADS[workload]
+        self.threads = self.oracle.hardware_threads()
+        self.arrays = self.oracle.synth_scene(seed, level_sizes(roots, levels, fanout), fanout, 0.0, self.threads)
+        self.n = int(self.arrays["position"].shape[0])
+        self.view, self.proj = camera(self.oracle, eye=CAMERA_EYE)
+        self.world = np.zeros((self.n, 16), np.float32)
+        self.mvp = np.zeros((self.n, 16), np.float32)
+        self.flags = np.zeros(self.n, np.uint8)
+        self.visible = np.zeros(self.n, np.uint32)
+        self.count = C.c_uint32(0)
+
+    def frame(self):
+        a, o, p = self.arrays, self.oracle, self._ptr
+        lo = a["level_offsets"]
+        o.lib.zo_scene_update(C.c_uint32(self.n), p(lo, np.uint32), C.c_uint32(lo.size - 1),
+                              p(a["position"], np.float32), p(a["rotation"], np.float32), p(a["scale"], np.float32),
+                              p(a["aabb_center"], np.float32), p(a["aabb_half"], np.float32), p(a["parent"], np.uint32),
+                              o._v(self.view, 16), o._v(self.proj, 16),
+                              p(self.world, np.float32), p(self.mvp, np.float32), p(self.flags, np.uint8),
+                              p(self.visible, np.uint32), C.byref(self.count), C.c_uint(self.threads))
+        return self.count.value
+
+
+def cpu_baseline(workload: str, budget_s: float = 12.0) -> dict:
+    sc = CpuScene(workload, BASE_SEED + 3)
+    sc.frame()   # first touch
+    frames, t0 = 0, time.perf_counter()
+    while True:
+        sc.frame()
+        frames += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or frames >= 50:
+            break
+    out = {"value": sc.n * frames / dt / 1e6, "unit": UNIT, "cores": sc.threads, "kind": "port",
+           "sample": f"{frames} frames of the full {sc.n:,}-entity {workload} scene, {sc.threads} host threads "
+                     f"splitting each level by entity range; {sc.kind_note}",
+           "ms_per_frame": dt / frames * 1e3}
+    del sc
+    from oracle.binding import LIB_REFERENCE
+    if os.path.exists(LIB_REFERENCE):
+        rs = CpuScene(workload, BASE_SEED + 3, reference_types=True)
+        rs.frame()
+        t0 = time.perf_counter()
+        rs.frame()
+        out["on_reference_types"] = {"value": rs.n / (time.perf_counter() - t0) / 1e6, "unit": UNIT,
+                                     "note": "same oracle on the reference's own vec3/vec4/mat4 (oracle/_ref), 1 frame"}
+    return out
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc = CpuScene(args.workload, BASE_SEED + 3)
+    for _ in range(max(args.warmup, 1)):
+        sc.frame()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        count = sc.frame()
+    dt = time.perf_counter() - t0
+    value = sc.n * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][3], "entities": sc.n, "camera_eye": CAMERA_EYE,
+                   "visible_fraction": count / sc.n, "where": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": sc.threads, "kind": "port",
+                         "sample": f"{args.steps} frames of the full {sc.n:,}-entity scene per run; {sc.kind_note}. "
+                                   "The upstream engine has no implementation of this path (SURVEY.md §0), so the oracle is the CPU arm."},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+class DevArray:
+    """Zero-copy view of a library-owned device buffer for torch (NCCL plumbing only)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<i4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import zenyth_b200 as zn
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world_size > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    roots, levels, fanout, desc = WORKLOADS[args.workload]
+    sizes = level_sizes(roots, levels, fanout)
+    E = sum(sizes)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+
+    # One explicit stream for everything: torch's current stream (events, NCCL) == the library's.
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx = zn.GpuContext(local_rank, stream=stream.cuda_stream)
+    scene = zn.Scene(ctx, E, offsets if levels > 1 else None)
+    scene.FillSynthetic(BASE_SEED + 3 + rank, fanout, 0.0)
+    cam = zn.Camera(zn.CameraDesc(eye=CAMERA_EYE, center=(CAMERA_EYE[0], CAMERA_EYE[1], CAMERA_EYE[2] - 1.0)))
+    scene.SetCamera(cam)
+    scene.SetIndexBase(rank * E if distributed and rank * E < 2 ** 32 else 0)
+    bufs = scene.DeviceBuffers()
+    launches_per_update = scene.LaunchesPerUpdate()
+
+    if distributed:
+        vis_t = torch.as_tensor(DevArray(bufs.visible, E), device=dev)
+        cnt_t = torch.as_tensor(DevArray(bufs.visible_count, 1), device=dev)
+        counts_all = torch.zeros(world_size, dtype=torch.int32, device=dev)
+        gathered = torch.empty(world_size * E, dtype=torch.int32, device=dev)
+
+    def step():
+        scene.Update()
+        if distributed:
+            # the one exchange of the path: counts, then the compacted index lists
+            dist.all_gather_into_tensor(counts_all, cnt_t)
+            m = int(counts_all.max().item())
+            dist.all_gather_into_tensor(gathered[: world_size * m], vis_t[:m])
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    visible = scene.VisibleCount()
+
+    gpu_id = str(torch.cuda.get_device_properties(dev).uuid)
+    if not gpu_id.startswith("GPU-"):
+        gpu_id = "GPU-" + gpu_id
+    sampler = ClockSampler(gpu_id)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record(stream)
+    for _ in range(args.steps):
+        step()
+    stop.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+
+    # ---- dominant kernel: last (largest) level, timed inside the library with CUDA events --------
+    scene.SetProfiling(True)
+    level_ms = []
+    tails = []
+    for _ in range(args.steps):
+        scene.Update()
+        lm, tail = scene.LevelTimesMs()
+        level_ms.append(lm)
+        tails.append(tail)
+    scene.SetProfiling(False)
+    level_ms = np.asarray(level_ms, np.float64)
+    dom = int(np.argmax(level_ms.mean(axis=0)))
+    dom_ms = float(level_ms[:, dom].mean())
+    dom_entities = int(sizes[dom])
+    dom_bytes = dom_entities * (188 if dom == 0 else 192)
+    peak, peak_src = measured_peaks()
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    frame_bytes = scene.AlgorithmicBytes(visible)
+    frame_ms_prof = float(level_ms.sum(axis=1).mean() + np.mean(tails))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+
+    # ---- e2e: the C-ABI call a CPU engine swaps in, HOST buffers, copies inside the timed region --
+    e2e = None
+    if not args.no_e2e:
+        inputs = scene.Inputs()
+        h_pos, h_rot, h_scl = (ctx.HostAlloc((E, 3), np.float32) for _ in range(3))
+        h_pos[:] = inputs["position"]; h_rot[:] = inputs["rotation"]; h_scl[:] = inputs["scale"]
+        del inputs
+        h_vis = ctx.HostAlloc((E,), np.uint32)
+        for _ in range(2):
+            n_vis = scene.FrameHost(h_pos, h_rot, h_scl, visible=h_vis)
+        barrier()
+        e2e_steps = args.steps
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            n_vis = scene.FrameHost(h_pos, h_rot, h_scl, visible=h_vis)
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world_size * E * e2e_steps / float(dt.item()) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(E) * 36, "d2h_bytes_per_step": int(n_vis) * 4 + 4,
+               "ms_per_step": float(dt.item()) / e2e_steps * 1e3,
+               "api": "zn_scene_frame_host: pinned host position/rotation/scale in, visible count + index list out; "
+                      "world/MVP stay device-resident for the renderer",
+               "timer": "host wall clock around the synchronous calls"}
+
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.workload)
+
+    if rank == 0:
+        value = world_size * E * args.steps / (total_ms * 1e-3) / 1e6
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "entities_per_gpu": E, "levels": levels, "camera_eye": CAMERA_EYE,
+                       "visible_fraction": visible / E,
+                       "l2": "inputs 1.07 GB + outputs 2.15 GB per step >> 126 MB L2, no flush needed" if E > 4_000_000
+                             else "footprint ~%d MB vs 126 MB L2" % (E * 192 // 1_000_000),
+                       "collective": "NCCL all_gather of visible counts + index lists per step" if distributed else "none (1 GPU)"},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": f"scene_level_kernel<{'true' if dom else 'false'}> level {dom} ({dom_entities:,} entities)",
+                         "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
+                         "frame": {"algorithmic_bytes": frame_bytes, "ms": total_ms / args.steps / (1 if not distributed else 1),
+                                   "achieved": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9,
+                                   "frac": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak,
+                                   "level_ms": [float(x) for x in level_ms.mean(axis=0)], "scan_emit_ms": float(np.mean(tails)),
+                                   "profiled_frame_ms": frame_ms_prof}},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": args.steps * launches_per_update,
+        }
+        print(json.dumps(line), flush=True)
+    scene.Close()
+    ctx.Close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="h8geo16m")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

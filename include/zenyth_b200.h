@@ -146,6 +146,12 @@ int zn_scene_frame_host(zn_scene* scene, zn_frame_host_io* io);
 int zn_scene_algorithmic_bytes(zn_scene* scene, uint32_t visible_count, uint64_t* out_bytes);
 /* Number of kernel launches one zn_scene_update enqueues. */
 int zn_scene_launches_per_update(zn_scene* scene, uint32_t* out_launches);
+/* Measurement support: when enabled, zn_scene_update brackets every level launch (and the
+ * compaction tail) with CUDA events on the context stream; zn_scene_level_times then returns the
+ * device time in milliseconds of each level kernel of the LAST update (out_ms[level_count]) and
+ * of the scan+emit tail (out_tail_ms, may be NULL).  Synchronises. */
+int zn_scene_set_profiling(zn_scene* scene, int enable);
+int zn_scene_level_times(zn_scene* scene, float* out_ms, uint32_t capacity, float* out_tail_ms);
 
 /* ---- mesh batch: bulk vertex position / normal transform by per-instance model matrices.
  *      pos' = model.transform_point(pos); nrm' = normalize(model.inverse_transpose().transform_normal(nrm))

@@ -81,6 +81,8 @@ PROTOTYPES = {
     "zn_scene_frame_host": (C.c_int, [vp, C.POINTER(FrameHostIO)]),
     "zn_scene_algorithmic_bytes": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint64)]),
     "zn_scene_launches_per_update": (C.c_int, [vp, c_u32_p]),
+    "zn_scene_set_profiling": (C.c_int, [vp, C.c_int]),
+    "zn_scene_level_times": (C.c_int, [vp, vp, C.c_uint32, c_float_p]),
     "zn_mesh_create": (C.c_int, [vp, C.POINTER(MeshDesc), C.POINTER(vp)]),
     "zn_mesh_destroy": (C.c_int, [vp]),
     "zn_mesh_set_vertices": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_size_t]),

@@ -76,6 +76,8 @@ struct zn_scene {
 	uint32_t* tile_mask = nullptr;       // [tiles][kTile/32]
 	uint32_t* tile_first_entity = nullptr; // [tiles]
 	uint32_t* host_count = nullptr;      // pinned [1]
+	bool profiling = false;
+	std::vector<cudaEvent_t> prof_events; // [levels+2]
 };
 
 struct zn_mesh_tile {

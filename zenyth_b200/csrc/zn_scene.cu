@@ -67,6 +67,11 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		prefetch_tensormap(&tm_mvp);
 	}
 
+	// ---- all global loads first (16 independent requests in flight per thread) ------------------
+	float v[15];
+#pragma unroll
+	for (int k = 0; k < 15; ++k) v[k] = ld_stream(in.comp[k] + ic);
+
 	// ---- parent range of this tile -> one bulk copy into shared memory -------------------------
 	uint32_t p = ZN_NO_PARENT;
 	uint32_t pmin = 0;
@@ -91,9 +96,6 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 	}
 
 	// ---- local TRS ------------------------------------------------------------------------------
-	float v[15];
-#pragma unroll
-	for (int k = 0; k < 15; ++k) v[k] = ld_stream(in.comp[k] + ic);
 	const Affine local = local_trs(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
 
 	// ---- world = parent.world * local -------------------------------------------------------------
@@ -374,6 +376,7 @@ int zn_scene_destroy(zn_scene* s) {
 	cudaFree(s->visible_count); cudaFree(s->tile_vis_count); cudaFree(s->tile_vis_offset); cudaFree(s->tile_mask);
 	cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
+	for (auto e : s->prof_events) cudaEventDestroy(e);
 	delete s;
 	return ZN_OK;
 }
@@ -452,8 +455,10 @@ int zn_scene_update(zn_scene* s) {
 	FrameConst fc;
 	std::memcpy(fc.vp, s->view_proj, sizeof(fc.vp));
 	std::memcpy(fc.planes, s->planes, sizeof(fc.planes));
+	const bool prof = s->profiling;
 	for (size_t l = 0; l < s->levels.size(); ++l) {
 		const zn_level& lv = s->levels[l];
+		if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[l], ctx->stream));
 		if (l == 0)
 			scene_level_kernel<false><<<lv.tiles, kTile, level_smem_bytes<false>(), ctx->stream>>>(
 				lv.tm_world, lv.tm_mvp, in, fc, s->world, lv.begin, lv.end, lv.tile_base, s->tile_vis_count, s->tile_mask);
@@ -461,11 +466,35 @@ int zn_scene_update(zn_scene* s) {
 			scene_level_kernel<true><<<lv.tiles, kTile, level_smem_bytes<true>(), ctx->stream>>>(
 				lv.tm_world, lv.tm_mvp, in, fc, s->world, lv.begin, lv.end, lv.tile_base, s->tile_vis_count, s->tile_mask);
 	}
+	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size()], ctx->stream));
 	scan_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(s->tile_vis_count, s->tile_vis_offset, s->tile_count, s->visible_count);
 	const uint32_t warps_per_cta = 8;
 	emit_visible_kernel<<<(s->tile_count + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(
 		s->tile_mask, s->tile_vis_offset, s->tile_first_entity, s->tile_count, s->index_base, s->visible);
+	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
 	ZN_CUDA(cudaGetLastError());
+	return ZN_OK;
+}
+
+int zn_scene_set_profiling(zn_scene* s, int enable) {
+	ZN_REQUIRE(s, "zn_scene_set_profiling: scene is NULL");
+	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	if (enable && s->prof_events.empty()) {
+		s->prof_events.resize(s->levels.size() + 2);
+		for (auto& e : s->prof_events) ZN_CUDA(cudaEventCreate(&e));
+	}
+	s->profiling = enable != 0;
+	return ZN_OK;
+}
+
+int zn_scene_level_times(zn_scene* s, float* out_ms, uint32_t capacity, float* out_tail_ms) {
+	ZN_REQUIRE(s && out_ms, "zn_scene_level_times: NULL argument");
+	ZN_REQUIRE(capacity >= s->levels.size(), "zn_scene_level_times: capacity %u < level_count %zu", capacity, s->levels.size());
+	if (!s->profiling || s->prof_events.empty()) return fail(ZN_ERR_STATE, "zn_scene_level_times: profiling is not enabled");
+	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	ZN_CUDA(cudaEventSynchronize(s->prof_events.back()));
+	for (size_t l = 0; l < s->levels.size(); ++l) ZN_CUDA(cudaEventElapsedTime(out_ms + l, s->prof_events[l], s->prof_events[l + 1]));
+	if (out_tail_ms) ZN_CUDA(cudaEventElapsedTime(out_tail_ms, s->prof_events[s->levels.size()], s->prof_events[s->levels.size() + 1]));
 	return ZN_OK;
 }
 

@@ -290,6 +290,17 @@ class Scene:
         check(self._lib.zn_scene_launches_per_update(self._h, C.byref(n)))
         return n.value
 
+    def SetProfiling(self, enable: bool) -> None:
+        check(self._lib.zn_scene_set_profiling(self._h, int(enable)))
+
+    def LevelTimesMs(self):
+        """(per-level kernel ms of the last Update, scan+emit tail ms); needs SetProfiling(True)."""
+        n = 1 if self.level_offsets is None else self.level_offsets.size - 1
+        out = np.zeros(n, np.float32)
+        tail = C.c_float()
+        check(self._lib.zn_scene_level_times(self._h, _p(out), n, C.byref(tail)))
+        return out, tail.value
+
     def Close(self) -> None:
         if getattr(self, "_h", None):
             self._lib.zn_scene_destroy(self._h)
