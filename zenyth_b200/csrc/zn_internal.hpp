@@ -30,6 +30,8 @@ int fail(int code, const char* fmt, ...);
 
 // Entities (or vertices /4) handled by one CTA.
 constexpr int kTile = 256;
+constexpr int kRows = 16;                         // rows of an input block
+constexpr uint32_t kBlockWords = kRows * kTile;   // 4096 words = 16 KiB per tile
 constexpr int kMeshTileVerts = 1024;
 
 // Builds a 2-D tensor map over a float[rows][16] matrix array: box {16, kTile}, 64-byte swizzle.
@@ -59,22 +61,27 @@ struct zn_scene {
 	std::vector<zn_level> levels;
 	uint32_t tile_count = 0;
 	uint32_t index_base = 0;
+	uint32_t epoch = 0;            // frame counter tagging the look-back tile states
+	int max_ctas = 0;              // co-resident CTAs of the persistent level kernel (4 per SM)
 	bool has_camera = false;
+	bool ranges_dirty = true;      // tile_prange must be rebuilt before the next update
 	float view_proj[16];
 	float planes[24];
-	// inputs, SoA: 15 float arrays + parent
-	float* soa = nullptr;          // [15][E_padded]
-	size_t soa_pitch = 0;          // elements between component arrays
-	uint32_t* parent = nullptr;    // [E]
+	// inputs: one 16 KiB block per 256-entity tile, rows = tx,ty,tz, pitch,yaw,roll, sx,sy,sz,
+	// aabb centre xyz, aabb half xyz (float) and parent (u32); tiles never straddle a level.
+	uint32_t* blocks = nullptr;    // [tiles][16][256]
+	uint2* tile_prange = nullptr;  // [tiles] {first parent, parent count} of the tile (count 0: none, 0xFFFFFFFF: gather)
 	// outputs
 	float* world = nullptr;        // [E][16]
 	float* mvp = nullptr;          // [E][16]
 	uint32_t* visible = nullptr;   // [E]
 	uint32_t* visible_count = nullptr; // [1] device
-	uint32_t* tile_vis_count = nullptr;  // [tiles]
-	uint32_t* tile_vis_offset = nullptr; // [tiles]
-	uint32_t* tile_mask = nullptr;       // [tiles][kTile/32]
+	uint32_t* tile_mask = nullptr;         // [tiles][8] visibility bits of the tile
 	uint32_t* tile_first_entity = nullptr; // [tiles]
+	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
+	unsigned long long* chunk_state = nullptr; // [chunks] look-back state: epoch<<34 | flag<<32 | value
+	uint32_t* ticket = nullptr;            // [1] monotonically increasing chunk ticket
+	uint32_t ticket_base = 0;              // tickets handed out by earlier frames
 	uint32_t* host_count = nullptr;      // pinned [1]
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events; // [levels+2]

@@ -1,18 +1,27 @@
-// zn_scene.cu — the per-frame scene update on sm_100a:
-//   K1/K2  scene_level_kernel<HAS_PARENT>: TRS -> local -> world (= parent.world * local) -> MVP,
-//          AABB-vs-frustum flag, per-tile visible count + bit mask.  One launch per hierarchy level.
-//   K3a    scan_tiles_kernel: exclusive scan of the per-tile counts (single CTA).
-//   K3b    emit_visible_kernel: ordered visible list from masks + offsets (warp per tile).
+// zn_scene.cu — the per-frame scene update on sm_100a.
 //
-// Data layout in HBM (DESIGN.md "Layout"): inputs are 15 scalar SoA arrays (tx,ty,tz, pitch,yaw,
-// roll, sx,sy,sz, aabb centre xyz, aabb half xyz) + parent[u32], so every warp load is one fully
-// coalesced 128-byte line; outputs are AoS float[E][16] (what mat4::data() consumers expect,
-// Core/include/math/matrix.hpp:60-61).  A thread owns one entity; its two 64-byte matrices go to
-// shared memory in the TMA 64-byte-swizzle pattern (conflict-free 16-byte stores) and leave the SM
-// as two cp.async.bulk.tensor stores per 256-entity tile, so HBM sees 16 KiB contiguous writes and
-// no thread ever issues a strided store.  Parent matrices of a tile are one contiguous range
-// (children are sorted by parent) fetched with a single cp.async.bulk into shared memory while
-// the threads are busy with sincos.
+//   scene_level_kernel<HAS_PARENT>  one launch per hierarchy level (K1/K2 of SURVEY.md §2):
+//       TRS -> local -> world (= parent.world * local) -> MVP -> AABB-vs-frustum flag, plus the
+//       tile's 256-bit visibility mask.
+//   emit_visible_kernel             one launch per frame (K3): ordered visible list from the masks,
+//       single pass — per-chunk popcount, decoupled look-back across chunks, ascending scatter.
+//
+// scene_level_kernel is PERSISTENT (4 CTAs of 256 threads per SM, each walking tiles b, b+G, ...)
+// and software-pipelined with the TMA unit:
+//   - a tile's inputs are ONE cp.async.bulk (SASS UBLKCP) of its 16 KiB tile-major block, plus one
+//     bulk copy of its contiguous parent-matrix range; thread 0 issues the copies for tile n+1 as
+//     soon as all threads have pulled tile n into registers, so HBM latency hides behind the
+//     sincos / matrix maths of tile n;
+//   - a thread owns one entity; its two 64-byte matrices go to shared memory in the TMA
+//     64-byte-swizzle pattern (conflict-free 16-byte stores) and the tile leaves as two
+//     cp.async.bulk.tensor stores (SASS UTMASTG) that drain while tile n+1 is computed.
+// No thread issues a global load or store for entity data; HBM sees 16 KiB bursts both ways.
+//
+// Data layout in HBM (DESIGN.md "Layout"): inputs are tile-major blocks — for every 256-entity
+// tile one contiguous 16 KiB record of 16 rows x 256 lanes (tx,ty,tz, pitch,yaw,roll, sx,sy,sz,
+// aabb centre xyz, aabb half xyz as float, parent as u32).  Tiles never straddle a hierarchy
+// level.  Outputs are AoS float[E][16] (what mat4::data() consumers expect,
+// Core/include/math/matrix.hpp:60-61), clipped at the level end by a per-level tensor map.
 #include "zn_internal.hpp"
 #include "zn_math.cuh"
 #include "zn_ptx.cuh"
@@ -22,230 +31,295 @@
 
 namespace zn {
 
-struct SceneIn {
-	const float* comp[15];
-	const uint32_t* parent;
-};
 struct FrameConst {
 	float vp[16];
 	float planes[24];
 };
 
-constexpr int kWarpsPerTile = kTile / 32;
-constexpr uint32_t kTileBytes = kTile * 64;   // one matrix tile
-
-template <bool HAS_PARENT>
-constexpr uint32_t level_smem_bytes() { return (HAS_PARENT ? 3u : 2u) * kTileBytes + 1024u; }
+constexpr int kWarpsPerTile = kTile / 32;                  // 8
+constexpr uint32_t kInBytes = kBlockWords * 4;             // 16 KiB input block
+constexpr uint32_t kParSlots = 64;                         // parent matrices staged per tile
+constexpr uint32_t kParBytes = kParSlots * 64;             // 4 KiB
+constexpr uint32_t kOutBytes = 2 * kTile * 64;             // world tile + mvp tile
+constexpr uint32_t kLevelSmem = kOutBytes + kInBytes + kParBytes + 1024;
+constexpr uint32_t kGather = 0xFFFFFFFFu;                  // tile_prange.y: parents too scattered to stage
+constexpr int kChunkTiles = 32;                            // tiles per emit CTA (8192 entities)
 
 template <bool HAS_PARENT>
 __global__ void __launch_bounds__(kTile, 4)
 scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_constant__ CUtensorMap tm_mvp,
-                   const __grid_constant__ SceneIn in, const __grid_constant__ FrameConst fc,
-                   const float* __restrict__ world_rd, uint32_t begin, uint32_t end, uint32_t tile_base,
-                   uint32_t* __restrict__ tile_vis_count, uint32_t* __restrict__ tile_mask) {
+                   const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
+                   const uint2* __restrict__ tile_prange, const float* __restrict__ world_rd,
+                   uint32_t begin, uint32_t end, uint32_t tile_base, uint32_t tiles,
+                   uint32_t* __restrict__ tile_mask) {
 	extern __shared__ uint8_t smem_raw[];
-	__shared__ uint64_t s_bar;
-	__shared__ uint32_t s_cnt[kWarpsPerTile];
-	__shared__ uint32_t s_pmin[kWarpsPerTile], s_pmax[kWarpsPerTile];
+	__shared__ uint64_t s_full;
+	__shared__ uint2 s_meta;
+	__shared__ uint32_t s_mask[kWarpsPerTile];
 
-	// 1024-byte aligned tiles (the swizzle pattern is a function of the shared address bits).
+	// 1024-byte aligned tiles (the swizzle pattern is a function of the shared address bits)
 	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-	float4* world_tile = reinterpret_cast<float4*>(smem);
-	float4* mvp_tile = reinterpret_cast<float4*>(smem + kTileBytes);
-	float4* parent_tile = reinterpret_cast<float4*>(smem + 2 * kTileBytes);
+	float4* out_world = reinterpret_cast<float4*>(smem);
+	float4* out_mvp = reinterpret_cast<float4*>(smem + kTile * 64);
+	const uint32_t* in_blk = reinterpret_cast<const uint32_t*>(smem + kOutBytes);
+	const float4* in_par = reinterpret_cast<const float4*>(smem + kOutBytes + kInBytes);
 
 	const int t = threadIdx.x;
 	const int lane = t & 31;
 	const int warp = t >> 5;
-	const uint32_t tile_first = begin + blockIdx.x * kTile;
-	const uint32_t i = tile_first + t;
-	const bool valid = i < end;
-	const uint32_t ic = valid ? i : end - 1;   // clamp: tail threads redo the last entity, rows >= end are clipped by TMA
+
+	// thread 0 is the TMA issuer: loads of tile `tl` into the (single) input stage
+	auto issue_loads = [&](uint32_t tl) {
+		const uint32_t gt = tile_base + tl;
+		uint2 pr = make_uint2(0u, 0u);
+		if (HAS_PARENT) pr = __ldg(tile_prange + gt);
+		const bool staged = HAS_PARENT && pr.y != 0u && pr.y != kGather;
+		s_meta = pr;
+		mbar_arrive_expect_tx(&s_full, kInBytes + (staged ? pr.y * 64u : 0u));
+		bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, kInBytes, &s_full);
+		if (staged) bulk_g2s(const_cast<float4*>(in_par), world_rd + size_t(pr.x) * 16, pr.y * 64u, &s_full);
+	};
 
 	if (t == 0) {
+		mbar_init(&s_full, 1);
+		fence_mbar_init();
 		prefetch_tensormap(&tm_world);
 		prefetch_tensormap(&tm_mvp);
+		issue_loads(blockIdx.x);
 	}
+	__syncthreads();
 
-	// ---- all global loads first (16 independent requests in flight per thread) ------------------
-	float v[15];
+	uint32_t n = 0;
+	for (uint32_t tl = blockIdx.x; tl < tiles; tl += gridDim.x, ++n) {
+		// ---- tile n: shared memory -> registers ------------------------------------------------
+		mbar_wait(&s_full, n & 1u);
+		float v[15];
 #pragma unroll
-	for (int k = 0; k < 15; ++k) v[k] = ld_stream(in.comp[k] + ic);
-
-	// ---- parent range of this tile -> one bulk copy into shared memory -------------------------
-	uint32_t p = ZN_NO_PARENT;
-	uint32_t pmin = 0;
-	bool staged = false;
-	if (HAS_PARENT) {
-		p = ld_stream(in.parent + ic);
-		const uint32_t lo = __reduce_min_sync(0xffffffffu, p);                               // NO_PARENT is UINT_MAX
-		const uint32_t hi = __reduce_max_sync(0xffffffffu, p == ZN_NO_PARENT ? 0u : p);
-		if (lane == 0) { s_pmin[warp] = lo; s_pmax[warp] = hi; }
-		if (t == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
-		__syncthreads();
-		uint32_t pmax = 0;
-		pmin = ZN_NO_PARENT;
-#pragma unroll
-		for (int k = 0; k < kWarpsPerTile; ++k) { pmin = min(pmin, s_pmin[k]); pmax = max(pmax, s_pmax[k]); }
-		staged = (pmin != ZN_NO_PARENT) && (pmax - pmin < uint32_t(kTile));
-		if (staged && t == 0) {
-			const uint32_t bytes = (pmax - pmin + 1u) * 64u;
-			mbar_arrive_expect_tx(&s_bar, bytes);
-			bulk_g2s(parent_tile, world_rd + size_t(pmin) * 16, bytes, &s_bar);
-		}
-	}
-
-	// ---- local TRS ------------------------------------------------------------------------------
-	const Affine local = local_trs(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
-
-	// ---- world = parent.world * local -------------------------------------------------------------
-	Affine w = local;
-	if (HAS_PARENT && p != ZN_NO_PARENT) {
-		float4 c0, c1, c2, c3;
-		if (staged) {
-			mbar_wait(&s_bar, 0);
-			const float4* src = parent_tile + size_t(p - pmin) * 4;
-			c0 = src[0]; c1 = src[1]; c2 = src[2]; c3 = src[3];
-		} else {
-			const float4* src = reinterpret_cast<const float4*>(world_rd) + size_t(p) * 4;
-			c0 = __ldg(src); c1 = __ldg(src + 1); c2 = __ldg(src + 2); c3 = __ldg(src + 3);
-		}
+		for (int k = 0; k < 15; ++k) v[k] = __uint_as_float(in_blk[k * kTile + t]);
+		const uint32_t p = HAS_PARENT ? in_blk[15 * kTile + t] : ZN_NO_PARENT;
 		Affine P;
-		P.m[0][0] = c0.x; P.m[1][0] = c0.y; P.m[2][0] = c0.z;
-		P.m[0][1] = c1.x; P.m[1][1] = c1.y; P.m[2][1] = c1.z;
-		P.m[0][2] = c2.x; P.m[1][2] = c2.y; P.m[2][2] = c2.z;
-		P.m[0][3] = c3.x; P.m[1][3] = c3.y; P.m[2][3] = c3.z;
-		w = affine_mul(P, local);
-	}
-
-	// ---- matrices -> swizzled shared tiles (chunk c of row t lives at chunk c ^ ((t>>1)&3)) -------
-	{
-		const int sw = (t >> 1) & 3;
-		float4* wr = world_tile + t * 4;
-		wr[0 ^ sw] = make_float4(w.m[0][0], w.m[1][0], w.m[2][0], 0.0f);
-		wr[1 ^ sw] = make_float4(w.m[0][1], w.m[1][1], w.m[2][1], 0.0f);
-		wr[2 ^ sw] = make_float4(w.m[0][2], w.m[1][2], w.m[2][2], 0.0f);
-		wr[3 ^ sw] = make_float4(w.m[0][3], w.m[1][3], w.m[2][3], 1.0f);
-		float m[16];
-		mvp_mul(fc.vp, w, m);
-		float4* mr = mvp_tile + t * 4;
-		mr[0 ^ sw] = make_float4(m[0], m[1], m[2], m[3]);
-		mr[1 ^ sw] = make_float4(m[4], m[5], m[6], m[7]);
-		mr[2 ^ sw] = make_float4(m[8], m[9], m[10], m[11]);
-		mr[3 ^ sw] = make_float4(m[12], m[13], m[14], m[15]);
-	}
-	fence_proxy_async_smem();
-
-	// ---- cull -------------------------------------------------------------------------------------
-	const bool vis = valid && aabb_visible(w, v[9], v[10], v[11], v[12], v[13], v[14], fc.planes);
-	const uint32_t mask = __ballot_sync(0xffffffffu, vis);
-	const uint32_t tile = tile_base + blockIdx.x;
-	if (lane == 0) {
-		s_cnt[warp] = __popc(mask);
-		tile_mask[size_t(tile) * kWarpsPerTile + warp] = mask;
-	}
-	__syncthreads();
-
-	if (t == 0) {
-		tensor_store_2d(&tm_world, world_tile, 0, int32_t(tile_first));
-		tensor_store_2d(&tm_mvp, mvp_tile, 0, int32_t(tile_first));
-		bulk_commit();
-		uint32_t c = 0;
-#pragma unroll
-		for (int k = 0; k < kWarpsPerTile; ++k) c += s_cnt[k];
-		tile_vis_count[tile] = c;
-		bulk_wait_read_all();
-	}
-}
-
-// Exclusive scan of n per-tile counts; one CTA of 1024 threads, 4 items per thread per pass.
-__global__ void __launch_bounds__(1024)
-scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t n,
-                  uint32_t* __restrict__ total) {
-	__shared__ uint32_t s_warp[32];
-	__shared__ uint32_t s_carry;
-	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	if (t == 0) s_carry = 0;
-	__syncthreads();
-	for (uint32_t base = 0; base < n; base += 4096) {
-		const uint32_t idx = base + t * 4;
-		uint32_t c[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) c[k] = (idx + k < n) ? counts[idx + k] : 0u;
-		const uint32_t mine = c[0] + c[1] + c[2] + c[3];
-		uint32_t incl = mine;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-			if (lane >= d) incl += y;
-		}
-		if (lane == 31) s_warp[warp] = incl;
-		__syncthreads();
-		if (warp == 0) {
-			uint32_t ws = s_warp[lane];
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const uint32_t y = __shfl_up_sync(0xffffffffu, ws, d);
-				if (lane >= d) ws += y;
+		if (HAS_PARENT && p != ZN_NO_PARENT) {
+			const uint2 pr = s_meta;
+			float4 c0, c1, c2, c3;
+			if (pr.y != kGather) {
+				const float4* src = in_par + size_t(p - pr.x) * 4;
+				c0 = src[0]; c1 = src[1]; c2 = src[2]; c3 = src[3];
+			} else {
+				const float4* src = reinterpret_cast<const float4*>(world_rd) + size_t(p) * 4;
+				c0 = __ldg(src); c1 = __ldg(src + 1); c2 = __ldg(src + 2); c3 = __ldg(src + 3);
 			}
-			s_warp[lane] = ws;   // inclusive over warps
+			P.m[0][0] = c0.x; P.m[1][0] = c0.y; P.m[2][0] = c0.z;
+			P.m[0][1] = c1.x; P.m[1][1] = c1.y; P.m[2][1] = c1.z;
+			P.m[0][2] = c2.x; P.m[1][2] = c2.y; P.m[2][2] = c2.z;
+			P.m[0][3] = c3.x; P.m[1][3] = c3.y; P.m[2][3] = c3.z;
 		}
-		__syncthreads();
-		const uint32_t carry = s_carry;
-		uint32_t excl = carry + (warp ? s_warp[warp - 1] : 0u) + incl - mine;
-#pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			if (idx + k < n) offsets[idx + k] = excl;
-			excl += c[k];
+		if (t == 0) bulk_wait_read_all();   // tile n-1's tensor stores have finished reading the out tile
+		__syncthreads();                    // input stage consumed by everyone; out tile free
+
+		// ---- prefetch tile n+1 while tile n is computed ------------------------------------------
+		if (t == 0 && tl + gridDim.x < tiles) issue_loads(tl + gridDim.x);
+
+		// ---- tile n: maths in registers ----------------------------------------------------------
+		const Affine local = local_trs(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+		Affine w = local;
+		if (HAS_PARENT && p != ZN_NO_PARENT) w = affine_mul(P, local);
+		const uint32_t first = begin + tl * kTile;
+		const bool vis = (first + t < end) && aabb_visible(w, v[9], v[10], v[11], v[12], v[13], v[14], fc.planes);
+		const uint32_t mask = __ballot_sync(0xffffffffu, vis);
+		if (lane == 0) s_mask[warp] = mask;
+
+		// ---- results -> swizzled shared tile (chunk c of row r lives at chunk c ^ ((r>>1)&3)) ------
+		{
+			const int sw = (t >> 1) & 3;
+			float4* wr = out_world + t * 4;
+			wr[0 ^ sw] = make_float4(w.m[0][0], w.m[1][0], w.m[2][0], 0.0f);
+			wr[1 ^ sw] = make_float4(w.m[0][1], w.m[1][1], w.m[2][1], 0.0f);
+			wr[2 ^ sw] = make_float4(w.m[0][2], w.m[1][2], w.m[2][2], 0.0f);
+			wr[3 ^ sw] = make_float4(w.m[0][3], w.m[1][3], w.m[2][3], 1.0f);
+			float m[16];
+			mvp_mul(fc.vp, w, m);
+			float4* mr = out_mvp + t * 4;
+			mr[0 ^ sw] = make_float4(m[0], m[1], m[2], m[3]);
+			mr[1 ^ sw] = make_float4(m[4], m[5], m[6], m[7]);
+			mr[2 ^ sw] = make_float4(m[8], m[9], m[10], m[11]);
+			mr[3 ^ sw] = make_float4(m[12], m[13], m[14], m[15]);
 		}
+		fence_proxy_async_smem();
 		__syncthreads();
-		if (t == 1023) s_carry = carry + s_warp[31];
-		__syncthreads();
+		if (t == 0) {
+			tensor_store_2d(&tm_world, out_world, 0, int32_t(first));
+			tensor_store_2d(&tm_mvp, out_mvp, 0, int32_t(first));
+			bulk_commit();
+		}
+		if (t < kWarpsPerTile) tile_mask[size_t(tile_base + tl) * kWarpsPerTile + t] = s_mask[t];
 	}
-	if (t == 0) *total = s_carry;
+	if (t == 0) bulk_wait_read_all();
 }
 
-// Ordered visible list: one warp per tile.
+// look-back chunk state: epoch (30 bits) | flag (2 bits) | value (32 bits)
+constexpr unsigned long long kFlagAggregate = 1, kFlagPrefix = 2;
+__device__ __forceinline__ unsigned long long pack_state(uint32_t epoch, unsigned long long flag, uint32_t value) {
+	return (static_cast<unsigned long long>(epoch) << 34) | (flag << 32) | value;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// Exclusive prefix of chunk `c` over all earlier chunks of this frame (decoupled look-back, one
+// warp).  Publishes the chunk's aggregate first so successors never wait on this chunk's prefix.
+__device__ __forceinline__ uint32_t chunk_exclusive_prefix(unsigned long long* state, uint32_t c, uint32_t total,
+                                                           uint32_t epoch, int lane) {
+	if (c == 0) {
+		if (lane == 0) st_state(state, pack_state(epoch, kFlagPrefix, total));
+		return 0;
+	}
+	if (lane == 0) st_state(state + c, pack_state(epoch, kFlagAggregate, total));
+	uint32_t prefix = 0;
+	int64_t window_end = int64_t(c) - 1;   // nearest predecessor not yet accounted for
+	while (true) {
+		const int64_t idx = window_end - lane;
+		unsigned long long st = pack_state(epoch, kFlagPrefix, 0);   // chunks before 0: prefix 0
+		if (idx >= 0) st = ld_state(state + idx);
+		const bool ready = (st >> 34) == epoch && ((st >> 32) & 3ull) != 0;
+		const bool is_prefix = ready && ((st >> 32) & 3ull) == kFlagPrefix;
+		const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
+		const uint32_t prefix_mask = __ballot_sync(0xffffffffu, is_prefix);
+		const uint32_t value = static_cast<uint32_t>(st);
+		if (prefix_mask) {
+			const int fp = __ffs(prefix_mask) - 1;                    // nearest chunk that knows its inclusive prefix
+			const uint32_t need = (fp == 31) ? 0xffffffffu : ((2u << fp) - 1u);
+			if ((ready_mask & need) == need) {
+				prefix += __reduce_add_sync(0xffffffffu, (lane <= fp) ? value : 0u);
+				break;
+			}
+		} else if (ready_mask == 0xffffffffu) {
+			prefix += __reduce_add_sync(0xffffffffu, value);
+			window_end -= 32;
+			continue;
+		}
+		__nanosleep(20);
+	}
+	if (lane == 0) st_state(state + c, pack_state(epoch, kFlagPrefix, prefix + total));
+	return prefix;
+}
+
+// Ordered visible list, single pass.  A CTA takes a ticket (chunks are claimed in start order, so
+// every predecessor of a running chunk is running or done), popcounts its 32 tiles' masks
+// (256 words), resolves its base by look-back, and scatters the set bits in ascending order.
 __global__ void __launch_bounds__(256)
-emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __restrict__ tile_offset,
-                    const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t index_base,
-                    uint32_t* __restrict__ visible) {
-	const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if (tile >= tiles) return;
-	const int lane = threadIdx.x & 31;
-	const uint32_t word = (lane < kWarpsPerTile) ? tile_mask[size_t(tile) * kWarpsPerTile + lane] : 0u;
+emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __restrict__ tile_first_entity,
+                    uint32_t tiles, uint32_t chunks, uint32_t epoch, uint32_t ticket_base, uint32_t* __restrict__ ticket,
+                    unsigned long long* __restrict__ chunk_state, uint32_t index_base,
+                    uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
+	__shared__ uint32_t s_chunk;
+	__shared__ uint32_t s_warp_total[8];
+	__shared__ uint32_t s_base;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	if (t == 0) s_chunk = atomicAdd(ticket, 1u) - ticket_base;
+	__syncthreads();
+	const uint32_t chunk = s_chunk;
+	// thread t owns mask word t of the chunk: tile chunk*32 + t/8, word t%8
+	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
+	const uint32_t word = (tile < tiles) ? tile_mask[size_t(tile) * kWarpsPerTile + (t & 7)] : 0u;
 	const uint32_t cnt = __popc(word);
 	uint32_t incl = cnt;
 #pragma unroll
-	for (int d = 1; d < kWarpsPerTile; d <<= 1) {
+	for (int d = 1; d < 32; d <<= 1) {
 		const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
 		if (lane >= d) incl += y;
 	}
-	const uint32_t excl = incl - cnt;
-	const uint32_t base = tile_offset[tile];
-	const uint32_t first = tile_first_entity[tile] + index_base;
-	const uint32_t lt = (1u << lane) - 1u;
+	if (lane == 31) s_warp_total[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t wt = (lane < 8) ? s_warp_total[lane] : 0u;
+		uint32_t winc = wt;
 #pragma unroll
-	for (int w = 0; w < kWarpsPerTile; ++w) {
-		const uint32_t m = __shfl_sync(0xffffffffu, word, w);
-		const uint32_t off = __shfl_sync(0xffffffffu, excl, w);
-		if ((m >> lane) & 1u) visible[base + off + __popc(m & lt)] = first + w * 32 + lane;
+		for (int d = 1; d < 8; d <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, winc, d);
+			if (lane >= d) winc += y;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, winc, 7);
+		if (lane < 8) s_warp_total[lane] = winc - wt;   // exclusive over warps
+		const uint32_t base = chunk_exclusive_prefix(chunk_state, chunk, total, epoch, lane);
+		if (lane == 0) {
+			s_base = base;
+			if (chunk == chunks - 1) *visible_count = base + total;
+		}
+	}
+	__syncthreads();
+	const uint32_t my_off = s_base + s_warp_total[warp] + incl - cnt;   // exclusive offset of this thread's word
+	const uint32_t first = (tile < tiles) ? tile_first_entity[tile] + index_base + (t & 7) * 32 : 0u;
+	// warp-cooperative scatter: word by word, lanes write the set bits in ascending order
+	const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 4
+	for (int w = 0; w < 32; ++w) {
+		const uint32_t mw = __shfl_sync(0xffffffffu, word, w);
+		if (mw == 0u) continue;
+		const uint32_t off = __shfl_sync(0xffffffffu, my_off, w);
+		const uint32_t f = __shfl_sync(0xffffffffu, first, w);
+		if ((mw >> lane) & 1u) visible[off + __popc(mw & lt)] = f + lane;
 	}
 }
 
-// Strided host records (3 floats every `stride_f` floats) -> three SoA component arrays.
-__global__ void repack3_kernel(const float* __restrict__ src, uint32_t stride_f, uint32_t count,
-                               float* __restrict__ dx, float* __restrict__ dy, float* __restrict__ dz) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count) return;
-	const float* s = src + size_t(i) * stride_f;
-	dx[i] = s[0]; dy[i] = s[1]; dz[i] = s[2];
+// {first parent, parent count} of every tile: one warp per tile over the parent row of its block.
+__global__ void __launch_bounds__(256)
+tile_prange_kernel(const uint32_t* __restrict__ blocks, uint32_t tiles, uint2* __restrict__ out) {
+	const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (tile >= tiles) return;
+	const int lane = threadIdx.x & 31;
+	const uint32_t* row = blocks + size_t(tile) * kBlockWords + 15 * kTile;
+	uint32_t lo = ZN_NO_PARENT, hi = 0;
+#pragma unroll
+	for (int k = 0; k < kTile / 32; ++k) {
+		const uint32_t p = row[k * 32 + lane];
+		lo = min(lo, p);
+		hi = max(hi, p == ZN_NO_PARENT ? 0u : p);
+	}
+	lo = __reduce_min_sync(0xffffffffu, lo);
+	hi = __reduce_max_sync(0xffffffffu, hi);
+	if (lane == 0) {
+		uint2 r = make_uint2(0u, 0u);
+		if (lo != ZN_NO_PARENT) r = make_uint2(lo, (hi - lo < kParSlots) ? hi - lo + 1u : kGather);
+		out[tile] = r;
+	}
 }
-__global__ void unpack3_kernel(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sz,
-                               uint32_t count, float* __restrict__ dst) {
+
+__global__ void init_parent_rows_kernel(uint32_t* __restrict__ blocks, uint32_t tiles) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count) return;
-	dst[size_t(i) * 3 + 0] = sx[i]; dst[size_t(i) * 3 + 1] = sy[i]; dst[size_t(i) * 3 + 2] = sz[i];
+	if (i < tiles * kTile) blocks[size_t(i / kTile) * kBlockWords + 15 * kTile + (i % kTile)] = ZN_NO_PARENT;
+}
+
+// Strided host records (3 words every `stride_w` words) of level-relative entities
+// [rel_first, rel_first+count) -> rows row0..row0+2 of the tile-major blocks.
+__global__ void repack3_kernel(const uint32_t* __restrict__ src, uint32_t stride_w, uint32_t count,
+                               uint32_t* __restrict__ blocks, uint32_t tile_base, uint32_t rel_first, int row0) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= count) return;
+	const uint32_t rel = rel_first + j;
+	uint32_t* d = blocks + size_t(tile_base + rel / kTile) * kBlockWords + row0 * kTile + (rel % kTile);
+	const uint32_t* s = src + size_t(j) * stride_w;
+	d[0] = s[0]; d[kTile] = s[1]; d[2 * kTile] = s[2];
+}
+__global__ void repack1_kernel(const uint32_t* __restrict__ src, uint32_t count, uint32_t* __restrict__ blocks,
+                               uint32_t tile_base, uint32_t rel_first, int row) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= count) return;
+	const uint32_t rel = rel_first + j;
+	blocks[size_t(tile_base + rel / kTile) * kBlockWords + row * kTile + (rel % kTile)] = src[j];
+}
+// rows row0..row0+nrows-1 of the blocks -> packed [count][nrows] words
+__global__ void unpack_kernel(const uint32_t* __restrict__ blocks, uint32_t tile_base, uint32_t rel_first, uint32_t count,
+                              int row0, int nrows, uint32_t* __restrict__ dst) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= count) return;
+	const uint32_t rel = rel_first + j;
+	const uint32_t* s = blocks + size_t(tile_base + rel / kTile) * kBlockWords + row0 * kTile + (rel % kTile);
+	for (int r = 0; r < nrows; ++r) dst[size_t(j) * nrows + r] = s[r * kTile];
 }
 
 static int ensure_staging(zn_ctx* ctx, size_t bytes) {
@@ -259,38 +333,58 @@ static int ensure_staging(zn_ctx* ctx, size_t bytes) {
 	return ZN_OK;
 }
 
-// Upload `count` strided 3-float records into SoA components [k0, k0+3) at entity offset `first`.
-static int upload3(zn_scene* s, int k0, uint32_t first, uint32_t count, const float* host, size_t stride_bytes) {
+// Calls fn(level, lo, hi) for every level that intersects entities [first, first+count).
+template <class F>
+static int for_each_level_range(zn_scene* s, uint32_t first, uint32_t count, F&& fn) {
+	const uint32_t last = first + count;
+	for (const zn_level& lv : s->levels) {
+		const uint32_t lo = std::max(first, lv.begin), hi = std::min(last, lv.end);
+		if (lo >= hi) continue;
+		const int rc = fn(lv, lo, hi);
+		if (rc != ZN_OK) return rc;
+	}
+	return ZN_OK;
+}
+
+// Upload `count` strided 3-float records into block rows [row0, row0+3) for entities from `first`.
+static int upload3(zn_scene* s, int row0, uint32_t first, uint32_t count, const float* host, size_t stride_bytes) {
 	if (!host || count == 0) return ZN_OK;
 	zn_ctx* ctx = s->ctx;
-	const uint32_t stride_f = uint32_t(stride_bytes / 4);
+	const uint32_t stride_w = uint32_t(stride_bytes / 4);
 	const uint32_t chunk = 1u << 22;   // records per pass: <= 64 MiB of staging at stride 16
 	int rc = ensure_staging(ctx, size_t(std::min(count, chunk)) * stride_bytes);
 	if (rc != ZN_OK) return rc;
 	for (uint32_t done = 0; done < count; done += chunk) {
 		const uint32_t n = std::min(chunk, count - done);
-		// the last record needs only 12 bytes, not a full stride
-		const size_t bytes = size_t(n - 1) * stride_bytes + 12;
+		const size_t bytes = size_t(n - 1) * stride_bytes + 12;   // the last record needs only 12 bytes
 		ZN_CUDA(cudaMemcpyAsync(ctx->staging, reinterpret_cast<const uint8_t*>(host) + size_t(done) * stride_bytes, bytes,
 		                        cudaMemcpyHostToDevice, ctx->stream));
-		float* d0 = s->soa + size_t(k0) * s->soa_pitch + first + done;
-		repack3_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->staging), stride_f, n, d0,
-		                                                        d0 + s->soa_pitch, d0 + 2 * s->soa_pitch);
+		const uint32_t chunk_first = first + done;
+		rc = for_each_level_range(s, chunk_first, n, [&](const zn_level& lv, uint32_t lo, uint32_t hi) {
+			const uint32_t* src = static_cast<const uint32_t*>(ctx->staging) + size_t(lo - chunk_first) * stride_w;
+			repack3_kernel<<<(hi - lo + 255) / 256, 256, 0, ctx->stream>>>(src, stride_w, hi - lo, s->blocks, lv.tile_base, lo - lv.begin, row0);
+			return ZN_OK;
+		});
+		if (rc != ZN_OK) return rc;
 		ZN_CUDA(cudaGetLastError());
 	}
 	return ZN_OK;
 }
 
-static int download3(zn_scene* s, int k0, uint32_t first, uint32_t count, float* host) {
+// Download block rows [row0, row0+nrows) of entities [first, first+count) as packed [count][nrows].
+static int download_rows(zn_scene* s, int row0, int nrows, uint32_t first, uint32_t count, void* host) {
 	if (!host || count == 0) return ZN_OK;
 	zn_ctx* ctx = s->ctx;
-	int rc = ensure_staging(ctx, size_t(count) * 12);
+	int rc = ensure_staging(ctx, size_t(count) * nrows * 4);
 	if (rc != ZN_OK) return rc;
-	const float* s0 = s->soa + size_t(k0) * s->soa_pitch + first;
-	unpack3_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(s0, s0 + s->soa_pitch, s0 + 2 * s->soa_pitch, count,
-	                                                            static_cast<float*>(ctx->staging));
+	rc = for_each_level_range(s, first, count, [&](const zn_level& lv, uint32_t lo, uint32_t hi) {
+		unpack_kernel<<<(hi - lo + 255) / 256, 256, 0, ctx->stream>>>(s->blocks, lv.tile_base, lo - lv.begin, hi - lo, row0, nrows,
+		                                                             static_cast<uint32_t*>(ctx->staging) + size_t(lo - first) * nrows);
+		return ZN_OK;
+	});
+	if (rc != ZN_OK) return rc;
 	ZN_CUDA(cudaGetLastError());
-	ZN_CUDA(cudaMemcpyAsync(host, ctx->staging, size_t(count) * 12, cudaMemcpyDeviceToHost, ctx->stream));
+	ZN_CUDA(cudaMemcpyAsync(host, ctx->staging, size_t(count) * nrows * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	ZN_CUDA(cudaStreamSynchronize(ctx->stream));
 	return ZN_OK;
 }
@@ -317,10 +411,23 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 		offs = {0u, E};
 	}
 	ZN_CUDA(cudaSetDevice(ctx->device));
+	static bool attr_set = false;
+	if (!attr_set) {
+		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLevelSmem)));
+		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLevelSmem)));
+		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+		attr_set = true;
+	}
 	zn_scene* s = new zn_scene();
 	s->ctx = ctx;
 	s->entity_count = E;
-	s->soa_pitch = (size_t(E) + 63) & ~size_t(63);
+	// Persistent grid: as many CTAs as fit at once.
+	int per_sm_a = 0, per_sm_b = 0;
+	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, scene_level_kernel<true>, kTile, kLevelSmem));
+	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, scene_level_kernel<false>, kTile, kLevelSmem));
+	s->max_ctas = std::min(per_sm_a, per_sm_b) * ctx->sm_count;
+	if (s->max_ctas < 1) { delete s; return fail(ZN_ERR_CUDA, "zn_scene_create: scene_level_kernel does not fit on an SM"); }
 	uint32_t tile_base = 0;
 	std::vector<uint32_t> tile_first;
 	for (size_t l = 0; l + 1 < offs.size(); ++l) {
@@ -334,35 +441,33 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 		s->levels.push_back(lv);
 	}
 	s->tile_count = tile_base;
+	s->chunk_count = (s->tile_count + kChunkTiles - 1) / kChunkTiles;
 	auto cleanup = [&](int rc) { zn_scene_destroy(s); return rc; };
 #define ZN_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return cleanup(fail(e_ == cudaErrorMemoryAllocation ? ZN_ERR_NOMEM : ZN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_))); } while (0)
-	ZN_TRY(cudaMalloc(&s->soa, s->soa_pitch * 15 * sizeof(float)));
-	ZN_TRY(cudaMalloc(&s->parent, size_t(E) * 4));
+	ZN_TRY(cudaMalloc(&s->blocks, size_t(s->tile_count) * kBlockWords * 4));
+	ZN_TRY(cudaMalloc(&s->tile_prange, size_t(s->tile_count) * sizeof(uint2)));
 	ZN_TRY(cudaMalloc(&s->world, size_t(E) * 64));
 	ZN_TRY(cudaMalloc(&s->mvp, size_t(E) * 64));
 	ZN_TRY(cudaMalloc(&s->visible, size_t(E) * 4));
 	ZN_TRY(cudaMalloc(&s->visible_count, 4));
-	ZN_TRY(cudaMalloc(&s->tile_vis_count, size_t(s->tile_count) * 4));
-	ZN_TRY(cudaMalloc(&s->tile_vis_offset, size_t(s->tile_count) * 4));
+	ZN_TRY(cudaMalloc(&s->chunk_state, size_t(s->chunk_count) * 8));
+	ZN_TRY(cudaMalloc(&s->ticket, 4));
 	ZN_TRY(cudaMalloc(&s->tile_mask, size_t(s->tile_count) * kWarpsPerTile * 4));
 	ZN_TRY(cudaMalloc(&s->tile_first_entity, size_t(s->tile_count) * 4));
 	ZN_TRY(cudaHostAlloc(&s->host_count, 4, cudaHostAllocDefault));
-	ZN_TRY(cudaMemsetAsync(s->soa, 0, s->soa_pitch * 15 * sizeof(float), ctx->stream));
-	ZN_TRY(cudaMemsetAsync(s->parent, 0xFF, size_t(E) * 4, ctx->stream));
-	ZN_TRY(cudaMemsetAsync(s->visible_count, 0, 4, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(s->blocks, 0, size_t(s->tile_count) * kBlockWords * 4, ctx->stream));
+	init_parent_rows_kernel<<<(s->tile_count * kTile + 255) / 256, 256, 0, ctx->stream>>>(s->blocks, s->tile_count);
+	ZN_TRY(cudaGetLastError());
+	ZN_TRY(cudaMemsetAsync(s->chunk_state, 0, size_t(s->chunk_count) * 8, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(s->ticket, 0, 4, ctx->stream));
 	ZN_TRY(cudaMemcpyAsync(s->tile_first_entity, tile_first.data(), tile_first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(s->visible_count, 0, 4, ctx->stream));
 	ZN_TRY(cudaStreamSynchronize(ctx->stream));
 #undef ZN_TRY
 	for (auto& lv : s->levels) {
 		int rc = encode_matrix_tensor_map(&lv.tm_world, s->world, lv.end);
 		if (rc == ZN_OK) rc = encode_matrix_tensor_map(&lv.tm_mvp, s->mvp, lv.end);
 		if (rc != ZN_OK) return cleanup(rc);
-	}
-	static bool attr_set = false;
-	if (!attr_set) {
-		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(level_smem_bytes<true>())));
-		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(level_smem_bytes<false>())));
-		attr_set = true;
 	}
 	*out_scene = s;
 	return ZN_OK;
@@ -372,9 +477,8 @@ int zn_scene_destroy(zn_scene* s) {
 	if (!s) return ZN_OK;
 	cudaSetDevice(s->ctx->device);
 	cudaStreamSynchronize(s->ctx->stream);
-	cudaFree(s->soa); cudaFree(s->parent); cudaFree(s->world); cudaFree(s->mvp); cudaFree(s->visible);
-	cudaFree(s->visible_count); cudaFree(s->tile_vis_count); cudaFree(s->tile_vis_offset); cudaFree(s->tile_mask);
-	cudaFree(s->tile_first_entity);
+	cudaFree(s->blocks); cudaFree(s->tile_prange); cudaFree(s->world); cudaFree(s->mvp); cudaFree(s->visible);
+	cudaFree(s->visible_count); cudaFree(s->chunk_state); cudaFree(s->ticket); cudaFree(s->tile_mask); cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
 	for (auto e : s->prof_events) cudaEventDestroy(e);
 	delete s;
@@ -415,6 +519,7 @@ int zn_scene_set_parents(zn_scene* s, uint32_t first, uint32_t count, const uint
 	int rc = check_range(s, first, count, "zn_scene_set_parents");
 	if (rc != ZN_OK) return rc;
 	ZN_REQUIRE(parent || count == 0, "zn_scene_set_parents: parent is NULL");
+	if (count == 0) return ZN_OK;
 	// validate the level-order contract on the host: a parent must live in an earlier level
 	size_t l = 0;
 	for (uint32_t k = 0; k < count; ++k) {
@@ -424,9 +529,24 @@ int zn_scene_set_parents(zn_scene* s, uint32_t first, uint32_t count, const uint
 		ZN_REQUIRE(p == ZN_NO_PARENT || p < s->levels[l].begin,
 		           "zn_scene_set_parents: entity %u (level %zu) has parent %u, which is not in an earlier level", i, l, p);
 	}
-	ZN_CUDA(cudaSetDevice(s->ctx->device));
-	ZN_CUDA(cudaMemcpyAsync(s->parent + first, parent, size_t(count) * 4, cudaMemcpyHostToDevice, s->ctx->stream));
-	ZN_CUDA(cudaStreamSynchronize(s->ctx->stream));
+	zn_ctx* ctx = s->ctx;
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	const uint32_t chunk = 1u << 24;
+	if ((rc = ensure_staging(ctx, size_t(std::min(count, chunk)) * 4)) != ZN_OK) return rc;
+	for (uint32_t done = 0; done < count; done += chunk) {
+		const uint32_t n = std::min(chunk, count - done);
+		ZN_CUDA(cudaMemcpyAsync(ctx->staging, parent + done, size_t(n) * 4, cudaMemcpyHostToDevice, ctx->stream));
+		const uint32_t chunk_first = first + done;
+		rc = for_each_level_range(s, chunk_first, n, [&](const zn_level& lv, uint32_t lo, uint32_t hi) {
+			repack1_kernel<<<(hi - lo + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->staging) + (lo - chunk_first),
+			                                                              hi - lo, s->blocks, lv.tile_base, lo - lv.begin, 15);
+			return ZN_OK;
+		});
+		if (rc != ZN_OK) return rc;
+		ZN_CUDA(cudaGetLastError());
+		ZN_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's array may be pageable and reused
+	}
+	s->ranges_dirty = true;
 	return ZN_OK;
 }
 
@@ -449,28 +569,33 @@ int zn_scene_update(zn_scene* s) {
 	if (!s->has_camera) return fail(ZN_ERR_STATE, "zn_scene_update: no camera set (call zn_scene_set_camera first)");
 	zn_ctx* ctx = s->ctx;
 	ZN_CUDA(cudaSetDevice(ctx->device));
-	SceneIn in;
-	for (int k = 0; k < 15; ++k) in.comp[k] = s->soa + size_t(k) * s->soa_pitch;
-	in.parent = s->parent;
+	if (s->ranges_dirty) {
+		tile_prange_kernel<<<(s->tile_count + 7) / 8, 256, 0, ctx->stream>>>(s->blocks, s->tile_count, s->tile_prange);
+		ZN_CUDA(cudaGetLastError());
+		s->ranges_dirty = false;
+	}
 	FrameConst fc;
 	std::memcpy(fc.vp, s->view_proj, sizeof(fc.vp));
 	std::memcpy(fc.planes, s->planes, sizeof(fc.planes));
 	const bool prof = s->profiling;
 	for (size_t l = 0; l < s->levels.size(); ++l) {
 		const zn_level& lv = s->levels[l];
+		const uint32_t grid = std::min<uint32_t>(lv.tiles, uint32_t(s->max_ctas));
 		if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[l], ctx->stream));
 		if (l == 0)
-			scene_level_kernel<false><<<lv.tiles, kTile, level_smem_bytes<false>(), ctx->stream>>>(
-				lv.tm_world, lv.tm_mvp, in, fc, s->world, lv.begin, lv.end, lv.tile_base, s->tile_vis_count, s->tile_mask);
+			scene_level_kernel<false><<<grid, kTile, kLevelSmem, ctx->stream>>>(
+				lv.tm_world, lv.tm_mvp, fc, s->blocks, s->tile_prange, s->world, lv.begin, lv.end, lv.tile_base, lv.tiles, s->tile_mask);
 		else
-			scene_level_kernel<true><<<lv.tiles, kTile, level_smem_bytes<true>(), ctx->stream>>>(
-				lv.tm_world, lv.tm_mvp, in, fc, s->world, lv.begin, lv.end, lv.tile_base, s->tile_vis_count, s->tile_mask);
+			scene_level_kernel<true><<<grid, kTile, kLevelSmem, ctx->stream>>>(
+				lv.tm_world, lv.tm_mvp, fc, s->blocks, s->tile_prange, s->world, lv.begin, lv.end, lv.tile_base, lv.tiles, s->tile_mask);
 	}
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size()], ctx->stream));
-	scan_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(s->tile_vis_count, s->tile_vis_offset, s->tile_count, s->visible_count);
-	const uint32_t warps_per_cta = 8;
-	emit_visible_kernel<<<(s->tile_count + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, ctx->stream>>>(
-		s->tile_mask, s->tile_vis_offset, s->tile_first_entity, s->tile_count, s->index_base, s->visible);
+	// ordered compaction: tickets keep counting across frames (ticket_base = tickets handed out so far)
+	s->epoch = (s->epoch % 0x3FFFFFFEu) + 1u;   // never 0: freshly allocated chunk states carry epoch 0
+	emit_visible_kernel<<<s->chunk_count, 256, 0, ctx->stream>>>(s->tile_mask, s->tile_first_entity, s->tile_count, s->chunk_count,
+	                                                             s->epoch, s->ticket_base, s->ticket, s->chunk_state, s->index_base,
+	                                                             s->visible, s->visible_count);
+	s->ticket_base += s->chunk_count;
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
 	ZN_CUDA(cudaGetLastError());
 	return ZN_OK;
@@ -500,7 +625,7 @@ int zn_scene_level_times(zn_scene* s, float* out_ms, uint32_t capacity, float* o
 
 int zn_scene_launches_per_update(zn_scene* s, uint32_t* out_launches) {
 	ZN_REQUIRE(s && out_launches, "zn_scene_launches_per_update: NULL argument");
-	*out_launches = uint32_t(s->levels.size()) + 2;
+	*out_launches = uint32_t(s->levels.size()) + 1;
 	return ZN_OK;
 }
 
@@ -562,12 +687,8 @@ int zn_scene_read_inputs(zn_scene* s, uint32_t first, uint32_t count, float* pos
 	ZN_CUDA(cudaSetDevice(s->ctx->device));
 	float* outs[5] = {position, rotation, scale, aabb_center, aabb_half};
 	for (int k = 0; k < 5; ++k)
-		if ((rc = download3(s, 3 * k, first, count, outs[k])) != ZN_OK) return rc;
-	if (parent && count) {
-		ZN_CUDA(cudaMemcpyAsync(parent, s->parent + first, size_t(count) * 4, cudaMemcpyDeviceToHost, s->ctx->stream));
-		ZN_CUDA(cudaStreamSynchronize(s->ctx->stream));
-	}
-	return ZN_OK;
+		if ((rc = download_rows(s, 3 * k, 3, first, count, outs[k])) != ZN_OK) return rc;
+	return download_rows(s, 15, 1, first, count, parent);
 }
 
 int zn_scene_device_buffers(zn_scene* s, zn_scene_buffers* out) {

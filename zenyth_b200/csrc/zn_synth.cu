@@ -19,11 +19,16 @@ __device__ __forceinline__ float synth_range(uint32_t seed, uint32_t index, uint
 	return add(lo, mul(u, span));
 }
 
-__global__ void synth_level_kernel(float* __restrict__ soa, size_t pitch, uint32_t* __restrict__ parent, uint32_t seed,
+__global__ void synth_level_kernel(uint32_t* __restrict__ blocks, uint32_t tile_base, uint32_t seed,
                                    uint32_t begin, uint32_t end, uint32_t prev_off, uint32_t prev_size, uint32_t fanout,
                                    int is_root, float center_range) {
-	const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t rel = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = begin + rel;
 	if (i >= end) return;
+	// tile-major input blocks: row k of this entity's tile, lane rel % kTile
+	float* soa = reinterpret_cast<float*>(blocks + size_t(tile_base + rel / kTile) * kBlockWords) + (rel % kTile) - i;
+	const size_t pitch = kTile;
+	uint32_t* parent = reinterpret_cast<uint32_t*>(soa) + 15 * pitch;
 	const float t_lo = is_root ? -1000.0f : -10.0f, t_span = is_root ? 2000.0f : 20.0f;
 	const float s_lo = is_root ? 0.5f : 0.9f, s_span = is_root ? 1.5f : 0.2f;
 #pragma unroll
@@ -72,9 +77,10 @@ int zn_scene_fill_synthetic(zn_scene* s, uint32_t seed, uint32_t fanout, float a
 		const uint32_t prev_off = l ? s->levels[l - 1].begin : 0;
 		const uint32_t prev_size = l ? s->levels[l - 1].end - s->levels[l - 1].begin : 0;
 		const uint32_t n = lv.end - lv.begin;
-		synth_level_kernel<<<(n + 255) / 256, 256, 0, s->ctx->stream>>>(s->soa, s->soa_pitch, s->parent, seed, lv.begin, lv.end,
+		synth_level_kernel<<<(n + 255) / 256, 256, 0, s->ctx->stream>>>(s->blocks, lv.tile_base, seed, lv.begin, lv.end,
 		                                                               prev_off, prev_size, fanout, l == 0 ? 1 : 0, aabb_center_range);
 	}
+	s->ranges_dirty = true;
 	ZN_CUDA(cudaGetLastError());
 	ZN_CUDA(cudaStreamSynchronize(s->ctx->stream));
 	return ZN_OK;
