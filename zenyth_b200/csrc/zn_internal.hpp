@@ -61,7 +61,6 @@ struct zn_scene {
 	std::vector<zn_level> levels;
 	uint32_t tile_count = 0;
 	uint32_t index_base = 0;
-	uint32_t epoch = 0;            // frame counter tagging the look-back tile states
 	int max_ctas = 0;              // co-resident CTAs of the persistent level kernel (4 per SM)
 	bool has_camera = false;
 	bool ranges_dirty = true;      // tile_prange must be rebuilt before the next update
@@ -79,9 +78,8 @@ struct zn_scene {
 	uint32_t* tile_mask = nullptr;         // [tiles][8] visibility bits of the tile
 	uint32_t* tile_first_entity = nullptr; // [tiles]
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
-	unsigned long long* chunk_state = nullptr; // [chunks] look-back state: epoch<<34 | flag<<32 | value
-	uint32_t* ticket = nullptr;            // [1] monotonically increasing chunk ticket
-	uint32_t ticket_base = 0;              // tickets handed out by earlier frames
+	uint32_t* chunk_total = nullptr;       // [chunks] visible count per chunk; zero between frames
+	uint32_t* done_counter = nullptr;      // [1] emit CTAs finished this frame
 	uint32_t* host_count = nullptr;      // pinned [1]
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events; // [levels+2]

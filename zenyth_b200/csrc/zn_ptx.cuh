@@ -67,6 +67,12 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // Wait until all committed bulk stores are complete (writes performed).
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// wait: block until the preceding kernel in the stream has completed and its writes are visible.
+// launch: allow the following kernel (launched with programmatic stream serialization) to start.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- cache-hinted global access ----------------------------------------------------------------
 __device__ __forceinline__ float ld_stream(const float* p) {
 	float v;

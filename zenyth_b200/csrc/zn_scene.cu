@@ -51,7 +51,7 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
                    const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
                    const uint2* __restrict__ tile_prange, const float* __restrict__ world_rd,
                    uint32_t begin, uint32_t end, uint32_t tile_base, uint32_t tiles,
-                   uint32_t* __restrict__ tile_mask) {
+                   uint32_t* __restrict__ tile_mask, uint32_t* __restrict__ chunk_total) {
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ uint64_t s_full;
 	__shared__ uint2 s_meta;
@@ -68,8 +68,10 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 	const int lane = t & 31;
 	const int warp = t >> 5;
 
-	// thread 0 is the TMA issuer: loads of tile `tl` into the (single) input stage
-	auto issue_loads = [&](uint32_t tl) {
+	// thread 0 is the TMA issuer: loads of tile `tl` into the (single) input stage.  `first_tile`:
+	// the input block does not depend on the previous level's kernel but the parent matrices do,
+	// so under programmatic dependent launch only the second copy waits for it.
+	auto issue_loads = [&](uint32_t tl, bool first_tile) {
 		const uint32_t gt = tile_base + tl;
 		uint2 pr = make_uint2(0u, 0u);
 		if (HAS_PARENT) pr = __ldg(tile_prange + gt);
@@ -77,6 +79,7 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		s_meta = pr;
 		mbar_arrive_expect_tx(&s_full, kInBytes + (staged ? pr.y * 64u : 0u));
 		bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, kInBytes, &s_full);
+		if (HAS_PARENT && first_tile) grid_dep_wait();
 		if (staged) bulk_g2s(const_cast<float4*>(in_par), world_rd + size_t(pr.x) * 16, pr.y * 64u, &s_full);
 	};
 
@@ -85,7 +88,8 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		fence_mbar_init();
 		prefetch_tensormap(&tm_world);
 		prefetch_tensormap(&tm_mvp);
-		issue_loads(blockIdx.x);
+		grid_dep_launch();          // the next level's kernel may start its own prologue now
+		issue_loads(blockIdx.x, true);
 	}
 	__syncthreads();
 
@@ -117,7 +121,7 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		__syncthreads();                    // input stage consumed by everyone; out tile free
 
 		// ---- prefetch tile n+1 while tile n is computed ------------------------------------------
-		if (t == 0 && tl + gridDim.x < tiles) issue_loads(tl + gridDim.x);
+		if (t == 0 && tl + gridDim.x < tiles) issue_loads(tl + gridDim.x, false);
 
 		// ---- tile n: maths in registers ----------------------------------------------------------
 		const Affine local = local_trs(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
@@ -151,81 +155,43 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 			tensor_store_2d(&tm_mvp, out_mvp, 0, int32_t(first));
 			bulk_commit();
 		}
-		if (t < kWarpsPerTile) tile_mask[size_t(tile_base + tl) * kWarpsPerTile + t] = s_mask[t];
+		if (warp == 0) {
+			const uint32_t gt = tile_base + tl;
+			const uint32_t word = (lane < kWarpsPerTile) ? s_mask[lane] : 0u;
+			if (lane < kWarpsPerTile) tile_mask[size_t(gt) * kWarpsPerTile + lane] = word;
+			const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(word));
+			if (lane == 0) atomicAdd(chunk_total + gt / kChunkTiles, cnt);
+		}
 	}
 	if (t == 0) bulk_wait_read_all();
 }
 
-// look-back chunk state: epoch (30 bits) | flag (2 bits) | value (32 bits)
-constexpr unsigned long long kFlagAggregate = 1, kFlagPrefix = 2;
-__device__ __forceinline__ unsigned long long pack_state(uint32_t epoch, unsigned long long flag, uint32_t value) {
-	return (static_cast<unsigned long long>(epoch) << 34) | (flag << 32) | value;
-}
-__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
-	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
-	unsigned long long v;
-	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-	return v;
-}
-
-// Exclusive prefix of chunk `c` over all earlier chunks of this frame (decoupled look-back, one
-// warp).  Publishes the chunk's aggregate first so successors never wait on this chunk's prefix.
-__device__ __forceinline__ uint32_t chunk_exclusive_prefix(unsigned long long* state, uint32_t c, uint32_t total,
-                                                           uint32_t epoch, int lane) {
-	if (c == 0) {
-		if (lane == 0) st_state(state, pack_state(epoch, kFlagPrefix, total));
-		return 0;
-	}
-	if (lane == 0) st_state(state + c, pack_state(epoch, kFlagAggregate, total));
-	uint32_t prefix = 0;
-	int64_t window_end = int64_t(c) - 1;   // nearest predecessor not yet accounted for
-	while (true) {
-		const int64_t idx = window_end - lane;
-		unsigned long long st = pack_state(epoch, kFlagPrefix, 0);   // chunks before 0: prefix 0
-		if (idx >= 0) st = ld_state(state + idx);
-		const bool ready = (st >> 34) == epoch && ((st >> 32) & 3ull) != 0;
-		const bool is_prefix = ready && ((st >> 32) & 3ull) == kFlagPrefix;
-		const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
-		const uint32_t prefix_mask = __ballot_sync(0xffffffffu, is_prefix);
-		const uint32_t value = static_cast<uint32_t>(st);
-		if (prefix_mask) {
-			const int fp = __ffs(prefix_mask) - 1;                    // nearest chunk that knows its inclusive prefix
-			const uint32_t need = (fp == 31) ? 0xffffffffu : ((2u << fp) - 1u);
-			if ((ready_mask & need) == need) {
-				prefix += __reduce_add_sync(0xffffffffu, (lane <= fp) ? value : 0u);
-				break;
-			}
-		} else if (ready_mask == 0xffffffffu) {
-			prefix += __reduce_add_sync(0xffffffffu, value);
-			window_end -= 32;
-			continue;
-		}
-		__nanosleep(20);
-	}
-	if (lane == 0) st_state(state + c, pack_state(epoch, kFlagPrefix, prefix + total));
-	return prefix;
-}
-
-// Ordered visible list, single pass.  A CTA takes a ticket (chunks are claimed in start order, so
-// every predecessor of a running chunk is running or done), popcounts its 32 tiles' masks
-// (256 words), resolves its base by look-back, and scatters the set bits in ascending order.
+// Ordered visible list, one pass over the 256-bit tile masks.  The level kernels have already
+// accumulated every chunk's visible count (chunk_total, one atomicAdd per tile), so an emit CTA
+// gets its base offset by summing the totals of the chunks before it — a few KiB of L2 reads, no
+// serial dependency between CTAs — then scatters its set bits in ascending order.  The last CTA to
+// finish re-zeroes the totals for the next frame.
 __global__ void __launch_bounds__(256)
 emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __restrict__ tile_first_entity,
-                    uint32_t tiles, uint32_t chunks, uint32_t epoch, uint32_t ticket_base, uint32_t* __restrict__ ticket,
-                    unsigned long long* __restrict__ chunk_state, uint32_t index_base,
-                    uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
-	__shared__ uint32_t s_chunk;
-	__shared__ uint32_t s_warp_total[8];
+                    uint32_t tiles, uint32_t chunks, uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ done_counter,
+                    uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
+	__shared__ uint32_t s_part[8];
+	__shared__ uint32_t s_warp_excl[8];
 	__shared__ uint32_t s_base;
+	__shared__ uint32_t s_last;
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	if (t == 0) s_chunk = atomicAdd(ticket, 1u) - ticket_base;
-	__syncthreads();
-	const uint32_t chunk = s_chunk;
+	const uint32_t chunk = blockIdx.x;
+	grid_dep_wait();   // masks and totals of every level are complete and visible
+
+	// base = sum of the totals of all earlier chunks
+	uint32_t acc = 0;
+	for (uint32_t j = t; j < chunk; j += 256) acc += __ldcg(chunk_total + j);
+	acc = __reduce_add_sync(0xffffffffu, acc);
+	if (lane == 0) s_part[warp] = acc;
+
 	// thread t owns mask word t of the chunk: tile chunk*32 + t/8, word t%8
 	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
-	const uint32_t word = (tile < tiles) ? tile_mask[size_t(tile) * kWarpsPerTile + (t & 7)] : 0u;
+	const uint32_t word = (tile < tiles) ? __ldcg(tile_mask + size_t(tile) * kWarpsPerTile + (t & 7)) : 0u;
 	const uint32_t cnt = __popc(word);
 	uint32_t incl = cnt;
 #pragma unroll
@@ -233,26 +199,26 @@ emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __re
 		const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
 		if (lane >= d) incl += y;
 	}
-	if (lane == 31) s_warp_total[warp] = incl;
+	if (lane == 31) s_warp_excl[warp] = incl;
 	__syncthreads();
 	if (warp == 0) {
-		uint32_t wt = (lane < 8) ? s_warp_total[lane] : 0u;
+		const uint32_t wt = (lane < 8) ? s_warp_excl[lane] : 0u;
 		uint32_t winc = wt;
 #pragma unroll
 		for (int d = 1; d < 8; d <<= 1) {
 			const uint32_t y = __shfl_up_sync(0xffffffffu, winc, d);
 			if (lane >= d) winc += y;
 		}
+		const uint32_t base = __reduce_add_sync(0xffffffffu, (lane < 8) ? s_part[lane] : 0u);
 		const uint32_t total = __shfl_sync(0xffffffffu, winc, 7);
-		if (lane < 8) s_warp_total[lane] = winc - wt;   // exclusive over warps
-		const uint32_t base = chunk_exclusive_prefix(chunk_state, chunk, total, epoch, lane);
+		if (lane < 8) s_warp_excl[lane] = winc - wt;
 		if (lane == 0) {
 			s_base = base;
 			if (chunk == chunks - 1) *visible_count = base + total;
 		}
 	}
 	__syncthreads();
-	const uint32_t my_off = s_base + s_warp_total[warp] + incl - cnt;   // exclusive offset of this thread's word
+	const uint32_t my_off = s_base + s_warp_excl[warp] + incl - cnt;   // exclusive offset of this thread's word
 	const uint32_t first = (tile < tiles) ? tile_first_entity[tile] + index_base + (t & 7) * 32 : 0u;
 	// warp-cooperative scatter: word by word, lanes write the set bits in ascending order
 	const uint32_t lt = (1u << lane) - 1u;
@@ -263,6 +229,18 @@ emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __re
 		const uint32_t off = __shfl_sync(0xffffffffu, my_off, w);
 		const uint32_t f = __shfl_sync(0xffffffffu, first, w);
 		if ((mw >> lane) & 1u) visible[off + __popc(mw & lt)] = f + lane;
+	}
+
+	// last CTA out re-zeroes the totals (every CTA has read them before it bumps the counter)
+	__syncthreads();
+	if (t == 0) {
+		__threadfence();
+		s_last = (atomicAdd(done_counter, 1u) == chunks - 1u) ? 1u : 0u;
+	}
+	__syncthreads();
+	if (s_last) {
+		for (uint32_t j = t; j < chunks; j += 256) chunk_total[j] = 0u;
+		if (t == 0) *done_counter = 0u;
 	}
 }
 
@@ -450,16 +428,16 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	ZN_TRY(cudaMalloc(&s->mvp, size_t(E) * 64));
 	ZN_TRY(cudaMalloc(&s->visible, size_t(E) * 4));
 	ZN_TRY(cudaMalloc(&s->visible_count, 4));
-	ZN_TRY(cudaMalloc(&s->chunk_state, size_t(s->chunk_count) * 8));
-	ZN_TRY(cudaMalloc(&s->ticket, 4));
+	ZN_TRY(cudaMalloc(&s->chunk_total, size_t(s->chunk_count) * 4));
+	ZN_TRY(cudaMalloc(&s->done_counter, 4));
 	ZN_TRY(cudaMalloc(&s->tile_mask, size_t(s->tile_count) * kWarpsPerTile * 4));
 	ZN_TRY(cudaMalloc(&s->tile_first_entity, size_t(s->tile_count) * 4));
 	ZN_TRY(cudaHostAlloc(&s->host_count, 4, cudaHostAllocDefault));
 	ZN_TRY(cudaMemsetAsync(s->blocks, 0, size_t(s->tile_count) * kBlockWords * 4, ctx->stream));
 	init_parent_rows_kernel<<<(s->tile_count * kTile + 255) / 256, 256, 0, ctx->stream>>>(s->blocks, s->tile_count);
 	ZN_TRY(cudaGetLastError());
-	ZN_TRY(cudaMemsetAsync(s->chunk_state, 0, size_t(s->chunk_count) * 8, ctx->stream));
-	ZN_TRY(cudaMemsetAsync(s->ticket, 0, 4, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(s->chunk_total, 0, size_t(s->chunk_count) * 4, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(s->done_counter, 0, 4, ctx->stream));
 	ZN_TRY(cudaMemcpyAsync(s->tile_first_entity, tile_first.data(), tile_first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	ZN_TRY(cudaMemsetAsync(s->visible_count, 0, 4, ctx->stream));
 	ZN_TRY(cudaStreamSynchronize(ctx->stream));
@@ -478,7 +456,7 @@ int zn_scene_destroy(zn_scene* s) {
 	cudaSetDevice(s->ctx->device);
 	cudaStreamSynchronize(s->ctx->stream);
 	cudaFree(s->blocks); cudaFree(s->tile_prange); cudaFree(s->world); cudaFree(s->mvp); cudaFree(s->visible);
-	cudaFree(s->visible_count); cudaFree(s->chunk_state); cudaFree(s->ticket); cudaFree(s->tile_mask); cudaFree(s->tile_first_entity);
+	cudaFree(s->visible_count); cudaFree(s->chunk_total); cudaFree(s->done_counter); cudaFree(s->tile_mask); cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
 	for (auto e : s->prof_events) cudaEventDestroy(e);
 	delete s;
@@ -578,26 +556,40 @@ int zn_scene_update(zn_scene* s) {
 	std::memcpy(fc.vp, s->view_proj, sizeof(fc.vp));
 	std::memcpy(fc.planes, s->planes, sizeof(fc.planes));
 	const bool prof = s->profiling;
+	// Levels >= 1 and the emit kernel are launched with programmatic stream serialization: their
+	// prologue (and the first input-block load) overlaps the tail of the kernel before them; they
+	// call griddepcontrol.wait before touching anything that kernel wrote.  Level 0 is a normal
+	// launch, so a frame never overlaps the previous frame's emit.
+	cudaLaunchAttribute pdl;
+	pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	pdl.val.programmaticStreamSerializationAllowed = 1;
+	cudaLaunchConfig_t cfg = {};
+	cfg.blockDim = dim3(kTile);
+	cfg.dynamicSmemBytes = kLevelSmem;
+	cfg.stream = ctx->stream;
+	cfg.attrs = &pdl;
 	for (size_t l = 0; l < s->levels.size(); ++l) {
 		const zn_level& lv = s->levels[l];
-		const uint32_t grid = std::min<uint32_t>(lv.tiles, uint32_t(s->max_ctas));
+		cfg.gridDim = dim3(std::min<uint32_t>(lv.tiles, uint32_t(s->max_ctas)));
+		cfg.numAttrs = (l == 0 || prof) ? 0 : 1;
 		if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[l], ctx->stream));
 		if (l == 0)
-			scene_level_kernel<false><<<grid, kTile, kLevelSmem, ctx->stream>>>(
-				lv.tm_world, lv.tm_mvp, fc, s->blocks, s->tile_prange, s->world, lv.begin, lv.end, lv.tile_base, lv.tiles, s->tile_mask);
+			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<false>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
+			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
+			                           s->tile_mask, s->chunk_total));
 		else
-			scene_level_kernel<true><<<grid, kTile, kLevelSmem, ctx->stream>>>(
-				lv.tm_world, lv.tm_mvp, fc, s->blocks, s->tile_prange, s->world, lv.begin, lv.end, lv.tile_base, lv.tiles, s->tile_mask);
+			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<true>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
+			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
+			                           s->tile_mask, s->chunk_total));
 	}
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size()], ctx->stream));
-	// ordered compaction: tickets keep counting across frames (ticket_base = tickets handed out so far)
-	s->epoch = (s->epoch % 0x3FFFFFFEu) + 1u;   // never 0: freshly allocated chunk states carry epoch 0
-	emit_visible_kernel<<<s->chunk_count, 256, 0, ctx->stream>>>(s->tile_mask, s->tile_first_entity, s->tile_count, s->chunk_count,
-	                                                             s->epoch, s->ticket_base, s->ticket, s->chunk_state, s->index_base,
-	                                                             s->visible, s->visible_count);
-	s->ticket_base += s->chunk_count;
+	cfg.gridDim = dim3(s->chunk_count);
+	cfg.blockDim = dim3(256);
+	cfg.dynamicSmemBytes = 0;
+	cfg.numAttrs = prof ? 0 : 1;
+	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, (const uint32_t*)s->tile_mask, (const uint32_t*)s->tile_first_entity,
+	                           s->tile_count, s->chunk_count, s->chunk_total, s->done_counter, s->index_base, s->visible, s->visible_count));
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
-	ZN_CUDA(cudaGetLastError());
 	return ZN_OK;
 }
 
