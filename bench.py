@@ -235,18 +235,16 @@ def run_ours(args) -> None:
     launches_per_update = scene.LaunchesPerUpdate()
 
     if distributed:
+        from zenyth_b200.distributed import VisibleGather
         vis_t = torch.as_tensor(DevArray(bufs.visible, E), device=dev)
         cnt_t = torch.as_tensor(DevArray(bufs.visible_count, 1), device=dev)
-        counts_all = torch.zeros(world_size, dtype=torch.int32, device=dev)
-        gathered = torch.empty(world_size * E, dtype=torch.int32, device=dev)
+        gather = VisibleGather(E, world_size, dev, torch.int32)
 
     def step():
         scene.Update()
         if distributed:
             # the one exchange of the path: counts, then the compacted index lists
-            dist.all_gather_into_tensor(counts_all, cnt_t)
-            m = int(counts_all.max().item())
-            dist.all_gather_into_tensor(gathered[: world_size * m], vis_t[:m])
+            gather.gather(vis_t, cnt_t)
 
     def barrier():
         if distributed:

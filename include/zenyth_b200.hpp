@@ -1,0 +1,280 @@
+// zenyth_b200.hpp — engine-idiom C++ host layer over the C ABI (include/zenyth_b200.h).
+//
+// The upstream engine declares no Transform / Scene / Camera / Mesh; these types are
+// what its frame loop would call, written in its own idiom: namespace Zenyth and PascalCase
+// methods for engine objects (Core/include/Application.hpp:7-53), `Desc` aggregates with defaults
+// (AppDesc, Application.hpp:9-14; WindowDesc, Window.hpp:36-41), `m_` members, [[nodiscard]],
+// deleted copies on owning objects (Application.hpp:21-24), std::runtime_error on failure
+// (Core/src/Application.cpp:28-30).  Maths types stay the reference's: anything with the layout
+// of zenyth::math::vec3 (16 bytes, Core/include/math/vector.hpp:69-72) or mat4 (64 bytes,
+// column-major, Core/include/math/matrix.hpp:66-69) passes through uncopied.
+//
+// Call sites in the reference's loop (Core/src/Application.cpp:41-52):
+//     OnUpdate(dt)  -> scene.SetTransforms(...dirty range...); scene.Update();
+//     OnRender()    -> scene.VisibleCount() / DeviceBuffers() feed the draw; mesh.Transform();
+// Header-only; link against libzenyth_b200.so.
+#pragma once
+
+#include "zenyth_b200.h"
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace Zenyth {
+
+namespace detail {
+inline void Check(int code, const char* what) {
+	if (code != ZN_OK) throw std::runtime_error(std::string(what) + " : " + zn_last_error());
+}
+} // namespace detail
+
+// Plain 3-float and 16-float carriers for callers that do not link the reference's math library.
+struct Float3 {
+	float x = 0.0f, y = 0.0f, z = 0.0f;
+};
+struct Mat4 {
+	float m[16] = {};   // column-major, element (r,c) at m[c*4+r]
+	[[nodiscard]] const float* data() const noexcept { return m; }
+	[[nodiscard]] float* data() noexcept { return m; }
+};
+
+// Local TRS of one entity.  rotation = (pitch, yaw, roll) radians, as mat4::from_euler
+// (Core/include/math/matrix.hpp:24); local = T * Ry(yaw)*Rx(pitch)*Rz(roll) * S.
+struct Transform {
+	Float3 position{0.0f, 0.0f, 0.0f};
+	Float3 rotation{0.0f, 0.0f, 0.0f};
+	Float3 scale{1.0f, 1.0f, 1.0f};
+};
+
+struct Aabb {
+	Float3 center{};
+	Float3 halfExtent{};
+};
+
+struct CameraDesc {
+	Float3 eye{0.0f, 0.0f, 0.0f};
+	Float3 center{0.0f, 0.0f, -1.0f};
+	Float3 up{0.0f, 1.0f, 0.0f};
+	float fovYRad = 1.04719755f;          // 60 degrees
+	float aspect = 1280.0f / 720.0f;      // Sandbox/include/SandboxApp.hpp:6
+	float nearZ = 0.1f;
+	float farZ = 5000.0f;
+};
+
+// View / projection pair.  Completes what mat4::look_at / mat4::perspective
+// (matrix.hpp:52-53, stubbed at matrix.cpp:107-113) would have produced.
+class Camera {
+public:
+	explicit Camera(const CameraDesc& desc = {}) : m_desc(desc) { Rebuild(); }
+
+	[[nodiscard]] const Mat4& View() const noexcept { return m_view; }
+	[[nodiscard]] const Mat4& Proj() const noexcept { return m_proj; }
+	[[nodiscard]] Mat4 ViewProj() const noexcept {
+		Mat4 vp;
+		zn_mat4_mul(m_proj.m, m_view.m, vp.m);
+		return vp;
+	}
+	[[nodiscard]] const CameraDesc& Desc() const noexcept { return m_desc; }
+
+	void LookAt(const Float3& eye, const Float3& center, const Float3& up) noexcept {
+		m_desc.eye = eye; m_desc.center = center; m_desc.up = up;
+		Rebuild();
+	}
+	// What IRenderer::Resize (Core/include/IRenderer.hpp:11) feeds.
+	void Resize(uint32_t width, uint32_t height) noexcept {
+		if (width == 0 || height == 0) return;   // same guard as Application.cpp:70
+		m_desc.aspect = static_cast<float>(width) / static_cast<float>(height);
+		Rebuild();
+	}
+
+private:
+	void Rebuild() noexcept {
+		zn_mat4_look_at(&m_desc.eye.x, &m_desc.center.x, &m_desc.up.x, m_view.m);
+		zn_mat4_perspective(m_desc.fovYRad, m_desc.aspect, m_desc.nearZ, m_desc.farZ, m_proj.m);
+	}
+	CameraDesc m_desc;
+	Mat4 m_view, m_proj;
+};
+
+// One per GPU.  Move-only, like every owning object in the reference.
+class GpuContext {
+public:
+	explicit GpuContext(int deviceOrdinal = 0) { detail::Check(zn_ctx_create(deviceOrdinal, &m_ctx), "GpuContext::GpuContext"); }
+	~GpuContext() { if (m_ctx) zn_ctx_destroy(m_ctx); }
+	GpuContext(const GpuContext&) = delete;
+	GpuContext& operator=(const GpuContext&) = delete;
+	GpuContext(GpuContext&& o) noexcept : m_ctx(std::exchange(o.m_ctx, nullptr)) {}
+	GpuContext& operator=(GpuContext&& o) noexcept {
+		if (this != &o) { if (m_ctx) zn_ctx_destroy(m_ctx); m_ctx = std::exchange(o.m_ctx, nullptr); }
+		return *this;
+	}
+
+	void SetStream(void* cudaStream) { detail::Check(zn_ctx_set_stream(m_ctx, cudaStream), "GpuContext::SetStream"); }
+	void Sync() { detail::Check(zn_ctx_sync(m_ctx), "GpuContext::Sync"); }
+	[[nodiscard]] zn_ctx* Handle() const noexcept { return m_ctx; }
+
+private:
+	zn_ctx* m_ctx = nullptr;
+};
+
+struct SceneDesc {
+	uint32_t entityCount = 0;
+	std::vector<uint32_t> levelOffsets;   // empty = one level of roots
+};
+
+// Level-ordered entity hierarchy resident on one GPU.
+class Scene {
+public:
+	Scene(GpuContext& ctx, const SceneDesc& desc) : m_entityCount(desc.entityCount) {
+		zn_scene_desc d{};
+		d.entity_count = desc.entityCount;
+		d.level_count = desc.levelOffsets.empty() ? 0u : static_cast<uint32_t>(desc.levelOffsets.size() - 1);
+		d.level_offsets = desc.levelOffsets.empty() ? nullptr : desc.levelOffsets.data();
+		detail::Check(zn_scene_create(ctx.Handle(), &d, &m_scene), "Scene::Scene");
+	}
+	~Scene() { if (m_scene) zn_scene_destroy(m_scene); }
+	Scene(const Scene&) = delete;
+	Scene& operator=(const Scene&) = delete;
+	Scene(Scene&& o) noexcept : m_scene(std::exchange(o.m_scene, nullptr)), m_entityCount(o.m_entityCount) {}
+
+	[[nodiscard]] uint32_t EntityCount() const noexcept { return m_entityCount; }
+
+	// Arrays of `count` records `strideBytes` apart: 12 for packed floats, 16 for arrays of
+	// zenyth::math::vec3, sizeof(Transform) for arrays of Transform (pass &t[0].position.x etc.).
+	void SetTransforms(uint32_t first, uint32_t count, const float* position, const float* rotation, const float* scale, size_t strideBytes) {
+		detail::Check(zn_scene_set_transforms(m_scene, first, count, position, rotation, scale, strideBytes), "Scene::SetTransforms");
+	}
+	void SetTransforms(uint32_t first, const std::vector<Transform>& t) {
+		if (t.empty()) return;
+		SetTransforms(first, static_cast<uint32_t>(t.size()), &t[0].position.x, &t[0].rotation.x, &t[0].scale.x, sizeof(Transform));
+	}
+	void SetTransform(uint32_t index, const Transform& t) {
+		SetTransforms(index, 1, &t.position.x, &t.rotation.x, &t.scale.x, sizeof(Transform));
+	}
+	void SetBounds(uint32_t first, uint32_t count, const float* center, const float* halfExtent, size_t strideBytes) {
+		detail::Check(zn_scene_set_bounds(m_scene, first, count, center, halfExtent, strideBytes), "Scene::SetBounds");
+	}
+	void SetBounds(uint32_t first, const std::vector<Aabb>& b) {
+		if (b.empty()) return;
+		SetBounds(first, static_cast<uint32_t>(b.size()), &b[0].center.x, &b[0].halfExtent.x, sizeof(Aabb));
+	}
+	void SetParents(uint32_t first, const std::vector<uint32_t>& parent) {
+		detail::Check(zn_scene_set_parents(m_scene, first, static_cast<uint32_t>(parent.size()), parent.data()), "Scene::SetParents");
+	}
+	void SetCamera(const Camera& camera) {
+		detail::Check(zn_scene_set_camera(m_scene, camera.View().m, camera.Proj().m), "Scene::SetCamera");
+	}
+	void SetIndexBase(uint32_t base) { detail::Check(zn_scene_set_index_base(m_scene, base), "Scene::SetIndexBase"); }
+
+	// One frame, asynchronous: world matrices over the hierarchy, MVP, visible list.
+	void Update() { detail::Check(zn_scene_update(m_scene), "Scene::Update"); }
+
+	[[nodiscard]] uint32_t VisibleCount() {
+		uint32_t n = 0;
+		detail::Check(zn_scene_visible_count(m_scene, &n), "Scene::VisibleCount");
+		return n;
+	}
+	[[nodiscard]] std::vector<uint32_t> Visible() {
+		std::vector<uint32_t> out(VisibleCount());
+		uint32_t n = 0;
+		detail::Check(zn_scene_read_visible(m_scene, out.data(), static_cast<uint32_t>(out.size()), &n), "Scene::Visible");
+		out.resize(n);
+		return out;
+	}
+	[[nodiscard]] std::vector<Mat4> World(uint32_t first, uint32_t count) {
+		std::vector<Mat4> out(count);
+		detail::Check(zn_scene_read_world(m_scene, first, count, count ? out[0].m : nullptr), "Scene::World");
+		return out;
+	}
+	[[nodiscard]] std::vector<Mat4> Mvp(uint32_t first, uint32_t count) {
+		std::vector<Mat4> out(count);
+		detail::Check(zn_scene_read_mvp(m_scene, first, count, count ? out[0].m : nullptr), "Scene::Mvp");
+		return out;
+	}
+	// Device-resident results for the renderer (no copy).
+	[[nodiscard]] zn_scene_buffers DeviceBuffers() {
+		zn_scene_buffers b{};
+		detail::Check(zn_scene_device_buffers(m_scene, &b), "Scene::DeviceBuffers");
+		return b;
+	}
+	[[nodiscard]] zn_scene* Handle() const noexcept { return m_scene; }
+
+private:
+	zn_scene* m_scene = nullptr;
+	uint32_t m_entityCount = 0;
+};
+
+struct MeshDesc {
+	uint32_t vertexCount = 0;
+	uint32_t instanceCount = 0;
+	std::vector<uint32_t> instanceFirstVertex;   // empty = equal ranges
+};
+
+// A batch of instanced vertices: positions and normals transformed by per-instance model matrices.
+class Mesh {
+public:
+	Mesh(GpuContext& ctx, const MeshDesc& desc) : m_vertexCount(desc.vertexCount) {
+		zn_mesh_desc d{};
+		d.vertex_count = desc.vertexCount;
+		d.instance_count = desc.instanceCount;
+		d.instance_first_vertex = desc.instanceFirstVertex.empty() ? nullptr : desc.instanceFirstVertex.data();
+		detail::Check(zn_mesh_create(ctx.Handle(), &d, &m_mesh), "Mesh::Mesh");
+	}
+	~Mesh() { if (m_mesh) zn_mesh_destroy(m_mesh); }
+	Mesh(const Mesh&) = delete;
+	Mesh& operator=(const Mesh&) = delete;
+	Mesh(Mesh&& o) noexcept : m_mesh(std::exchange(o.m_mesh, nullptr)), m_vertexCount(o.m_vertexCount) {}
+
+	void SetVertices(uint32_t first, uint32_t count, const float* position, const float* normal, size_t strideBytes) {
+		detail::Check(zn_mesh_set_vertices(m_mesh, first, count, position, normal, strideBytes), "Mesh::SetVertices");
+	}
+	void SetModels(uint32_t first, const std::vector<Mat4>& models) {
+		if (models.empty()) return;
+		detail::Check(zn_mesh_set_models(m_mesh, first, static_cast<uint32_t>(models.size()), models[0].m), "Mesh::SetModels");
+	}
+	// Use world matrices [firstEntity, firstEntity + instanceCount) of a scene as the models.
+	void BindSceneModels(Scene& scene, uint32_t firstEntity) {
+		detail::Check(zn_mesh_bind_scene_models(m_mesh, scene.Handle(), firstEntity), "Mesh::BindSceneModels");
+	}
+	void Transform() { detail::Check(zn_mesh_transform(m_mesh), "Mesh::Transform"); }
+	void Read(uint32_t first, uint32_t count, float* outPosition, float* outNormal) {
+		detail::Check(zn_mesh_read(m_mesh, first, count, outPosition, outNormal), "Mesh::Read");
+	}
+	[[nodiscard]] zn_mesh_buffers DeviceBuffers() {
+		zn_mesh_buffers b{};
+		detail::Check(zn_mesh_device_buffers(m_mesh, &b), "Mesh::DeviceBuffers");
+		return b;
+	}
+	[[nodiscard]] uint32_t VertexCount() const noexcept { return m_vertexCount; }
+
+private:
+	zn_mesh* m_mesh = nullptr;
+	uint32_t m_vertexCount = 0;
+};
+
+// The reference's plugin seam, in its four-method shape (Core/include/IRenderer.hpp:5-12), with a
+// portable handle in place of HWND.  A D3D12 (or any) renderer owns one of these beside its swap
+// chain: BeginFrame runs the scene update the draw depends on, EndFrame leaves world / MVP /
+// visible list on the device for the draw submission.
+class SceneRenderer {
+public:
+	SceneRenderer(Scene& scene, Camera& camera) : m_scene(scene), m_camera(camera) {}
+	void Init(void* /*nativeWindowHandle*/, uint32_t width, uint32_t height) { Resize(width, height); }
+	void BeginFrame() {
+		m_scene.SetCamera(m_camera);
+		m_scene.Update();
+	}
+	void EndFrame() { m_visibleCount = m_scene.VisibleCount(); }
+	void Resize(uint32_t width, uint32_t height) { m_camera.Resize(width, height); }
+	[[nodiscard]] uint32_t VisibleCount() const noexcept { return m_visibleCount; }
+
+private:
+	Scene& m_scene;
+	Camera& m_camera;
+	uint32_t m_visibleCount = 0;
+};
+
+} // namespace Zenyth

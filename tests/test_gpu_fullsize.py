@@ -1,0 +1,95 @@
+"""-m gpu: BASELINE.json's full-size configurations.  The CPU oracle finishes a 16.7M-entity frame
+in a fraction of a second on the GPU box's host cores, so configs[2] is compared entity for entity;
+the 64Mi-vertex mesh batch (configs[3]) is compared chunk by chunk; on top come the
+size-independent properties the domain offers (ascending unique visible list, count == popcount,
+idempotence, children follow a moved root)."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import rel_err, same_values
+from oracle.binding import BASE_SEED, camera, h8_geo_level_sizes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_h8geo_16m_entity_for_entity(oracle, gpu_ctx):
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 8)
+    E = sum(sizes)
+    assert E == 16_777_215
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.0)
+    view, proj = camera(oracle, eye=(0, 0, 1500))
+    ref = oracle.scene_update(arrays, view, proj, threads=oracle.hardware_threads())
+
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.FillSynthetic(BASE_SEED + 3, 8, 0.0)              # device-side generator, same bits as the host's
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    sc.Update()
+    vis = sc.Visible()
+    # properties
+    assert vis.size == sc.VisibleCount() and np.all(np.diff(vis.astype(np.int64)) > 0) and vis[-1] < E
+    # parity, exact
+    assert np.array_equal(vis, ref["visible"])
+    step = 1 << 21
+    for first in range(0, E, step):
+        n = min(step, E - first)
+        w, m = sc.World(first, n), sc.Mvp(first, n)
+        assert rel_err(w, ref["world"][first:first + n]) <= 1e-5 and same_values(w, ref["world"][first:first + n]), first
+        assert rel_err(m, ref["mvp"][first:first + n]) <= 1e-5 and same_values(m, ref["mvp"][first:first + n]), first
+    # idempotence
+    sc.Update()
+    assert np.array_equal(sc.Visible(), vis)
+    # moving a root by d moves its whole subtree's world translation by d (to rounding), nothing else
+    d = np.float32([128.0, -64.0, 32.0])
+    root = 3
+    moved = arrays["position"][root:root + 1] + d
+    sc.SetTransforms(position=moved, first=root, count=1)
+    sc.Update()
+    last = sc.World(E - 4096, 4096)          # tail of the deepest level: descendants of the last root (6)
+    assert same_values(last, ref["world"][E - 4096:])
+    lvl7 = int(arrays["level_offsets"][7])
+    per_root = sizes[7] // 7
+    sub = sc.World(lvl7 + root * per_root, 1024)[:, 12:15]
+    want = ref["world"][lvl7 + root * per_root: lvl7 + root * per_root + 1024, 12:15] + d
+    assert np.abs(sub - want).max() <= 1e-3    # positions ~1e3: one float32 ulp is 6e-5
+    sc.Close()
+
+
+def test_mesh_64m_vertices_chunked(oracle, gpu_ctx):
+    import zenyth_b200 as zn
+    I, verts = 65536, 1024
+    V = I * verts
+    flat = oracle.synth_scene(BASE_SEED + 2, [I], fanout=1)
+    flat["parent"] = None
+    flat["level_offsets"] = None
+    view, proj = camera(oracle)
+    models = oracle.scene_update(flat, view, proj, threads=oracle.hardware_threads(), want_mvp=False)["world"]
+    mesh = zn.Mesh(gpu_ctx, V, I)
+    mesh.FillSynthetic(BASE_SEED + 4)
+    mesh.SetModels(models)
+    mesh.Transform()
+    pos, nrm = oracle.synth_mesh(BASE_SEED + 4, V)
+    chunk_inst = 8192
+    for i0 in range(0, I, chunk_inst * 2):   # every other 8M-vertex chunk: 32M vertices compared exactly
+        v0, n = i0 * verts, chunk_inst * verts
+        first = (np.arange(chunk_inst + 1, dtype=np.uint32) * verts).astype(np.uint32)
+        rp, rn = oracle.mesh_transform(first, models[i0:i0 + chunk_inst], pos[v0:v0 + n], nrm[v0:v0 + n], threads=oracle.hardware_threads())
+        gp, gn = mesh.Read(v0, n)
+        assert same_values(gp, rp) and same_values(gn, rn), i0
+    gp, gn = mesh.Read(V - 4096, 4096)
+    assert np.abs(np.linalg.norm(gn.astype(np.float64), axis=1) - 1.0).max() < 3e-7
+    mesh.Close()
+
+
+def test_cpp_headless_sandbox_runs_the_reference_loop_shape(gpu_ctx):
+    """config 1 stand-in: 4,681-entity 5-level tree through the C++ wrapper."""
+    import json
+
+    from zenyth_b200 import build as zb
+    exe = zb.build_host()
+    r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["entities"] == 4681 and 0 < out["visible"] <= 4681 and out["ms_per_frame"] > 0

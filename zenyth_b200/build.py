@@ -61,5 +61,27 @@ def build(verbose: bool = False, force: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_SRC = os.path.join(PKG, "host", "sandbox_headless.cpp")
+HOST_EXE = os.path.join(PKG, "host", "sandbox_headless")
+
+
+def build_host(force: bool = False) -> str:
+    """The headless C++ Sandbox over include/zenyth_b200.hpp (plain g++, no nvcc)."""
+    build()
+    inc = os.path.join(PKG, "..", "include")
+    deps = [HOST_SRC, os.path.join(inc, "zenyth_b200.hpp"), os.path.join(inc, "zenyth_b200.h"), LIB_PATH]
+    if not force and os.path.exists(HOST_EXE) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_EXE) for d in deps):
+        return HOST_EXE
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-I", inc, HOST_SRC, "-L", LIB_DIR, "-lzenyth_b200",
+           "-Wl,-rpath,$ORIGIN/../lib", "-o", HOST_EXE]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("g++ failed building sandbox_headless")
+    return HOST_EXE
+
+
 if __name__ == "__main__":
     print(build(verbose="--verbose" in sys.argv, force=True))
+    print(build_host(force=True))
