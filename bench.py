@@ -234,17 +234,30 @@ def run_ours(args) -> None:
     bufs = scene.DeviceBuffers()
     launches_per_update = scene.LaunchesPerUpdate()
 
+    frame_no = [0]
     if distributed:
-        from zenyth_b200.distributed import VisibleGather
-        vis_t = torch.as_tensor(DevArray(bufs.visible, E), device=dev)
-        cnt_t = torch.as_tensor(DevArray(bufs.visible_count, 1), device=dev)
-        gather = VisibleGather(E, world_size, dev, torch.int32)
+        # The one exchange of the path: all-gather the visible counts, then the
+        # compacted index lists.  Double-buffered: the scene writes frame k's list straight into
+        # slot k%2 of the exchange, whose NCCL all-gathers run on the collective's stream while
+        # frame k+1 is computed; a slot is collected (checked, exact) before it is reused.
+        from zenyth_b200.distributed import VisibleExchange
+        exchange = VisibleExchange(E, world_size, dev, torch.int32, slots=2)
 
     def step():
-        scene.Update()
         if distributed:
-            # the one exchange of the path: counts, then the compacted index lists
-            gather.gather(vis_t, cnt_t)
+            slot = frame_no[0] % 2
+            exchange.acquire(slot)
+            scene.BindVisibleOutput(exchange.local_ptr(slot), E, exchange.count_ptr(slot))
+            scene.Update()
+            exchange.launch(slot)
+        else:
+            scene.Update()
+        frame_no[0] += 1
+
+    def finish():
+        """All frames issued so far are complete, including their exchanges."""
+        if distributed:
+            exchange.drain()
 
     def barrier():
         if distributed:
@@ -253,7 +266,11 @@ def run_ours(args) -> None:
 
     for _ in range(max(args.warmup, 3)):
         step()
+    finish()
     barrier()
+    if distributed:
+        scene.BindVisibleOutput(None)
+        scene.Update()
     visible = scene.VisibleCount()
 
     gpu_id = str(torch.cuda.get_device_properties(dev).uuid)
@@ -265,9 +282,12 @@ def run_ours(args) -> None:
     start.record(stream)
     for _ in range(args.steps):
         step()
+    finish()                  # the stream now also waits for the last exchanges
     stop.record(stream)
     barrier()
     clocks = sampler.stop()
+    if distributed:
+        scene.BindVisibleOutput(None)
     ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -338,7 +358,9 @@ def run_ours(args) -> None:
                        "visible_fraction": visible / E,
                        "l2": "inputs 1.07 GB + outputs 2.15 GB per step >> 126 MB L2, no flush needed" if E > 4_000_000
                              else "footprint ~%d MB vs 126 MB L2" % (E * 192 // 1_000_000),
-                       "collective": "NCCL all_gather of visible counts + index lists per step" if distributed else "none (1 GPU)"},
+                       "collective": ("NCCL all_gather of visible counts + index lists every step, double-buffered: the exchange of "
+                                      "frame k overlaps the update of frame k+1; the timed region ends after the last exchange; "
+                                      f"re-gathers after a size misprediction: {exchange.regathers}") if distributed else "none (1 GPU)"},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,

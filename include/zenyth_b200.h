@@ -102,6 +102,11 @@ int zn_scene_set_bounds(zn_scene* scene, uint32_t first, uint32_t count,
 int zn_scene_set_parents(zn_scene* scene, uint32_t first, uint32_t count, const uint32_t* parent);
 /* view and proj exactly as mat4::data() (matrix.hpp:60-61). */
 int zn_scene_set_camera(zn_scene* scene, const float view[16], const float proj[16]);
+/* Redirect the visible list + count of subsequent updates into caller-owned DEVICE memory (for
+ * example a slot of a double-buffered all-gather input, so a collective can consume frame k while
+ * frame k+1 is computed).  capacity (in indices) must be >= entity_count.  Both NULL restores the
+ * scene's own buffers. */
+int zn_scene_bind_visible_output(zn_scene* scene, void* visible_dev, uint32_t capacity, void* visible_count_dev);
 /* Added to every index written to the visible list (shard -> global numbering). */
 int zn_scene_set_index_base(zn_scene* scene, uint32_t index_base);
 

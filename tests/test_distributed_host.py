@@ -67,6 +67,35 @@ def _worker(rank: int, world: int, port: int, capacity: int, out_dir: str):
         merged = VisibleGather.concatenate(counts, lists).numpy()
         ok &= bool(np.array_equal(merged, np.concatenate(expect)))
         ok &= bool(np.all(np.diff(merged) > 0))              # global list ascending
+    # the pipelined exchange: two slots, sizes predicted from the last collected frame; frame 3
+    # grows past the prediction on rank 0 and must be re-gathered exactly
+    from zenyth_b200.distributed import VisibleExchange
+    ex = VisibleExchange(capacity, world, "cpu", torch.int32, slots=2, headroom=0.0)
+    results = {}
+
+    def frame_list(frame, r):
+        base = _rank_list(r, capacity)
+        if frame == 3 and r == 0:
+            return np.arange(capacity, dtype=np.int32)          # suddenly everything is visible
+        if frame == 4 and r == 1:
+            return base[:0]
+        return base[: max(1, base.size - 10 * frame)]
+
+    for frame in range(6):
+        slot = frame % 2
+        got = ex.acquire(slot)
+        if got is not None:
+            results[frame - 2] = [got[1][r, : got[0][r]].numpy().copy() for r in range(world)]
+        mine = frame_list(frame, rank)
+        ex.local[slot][: mine.size] = torch.from_numpy(mine)
+        ex.local_count[slot][0] = mine.size
+        ex.launch(slot)
+    for frame, got in zip((4, 5), ex.drain()):       # slot 0 holds frame 4, slot 1 frame 5
+        results[frame] = [got[1][r, : got[0][r]].numpy().copy() for r in range(world)]
+    for frame in range(6):
+        for r in range(world):
+            ok &= bool(np.array_equal(results[frame][r], frame_list(frame, r)))
+    ok &= ex.regathers >= 1
     with open(os.path.join(out_dir, f"rank{rank}.ok"), "w") as f:
         f.write("1" if ok else "0")
     dist.destroy_process_group()
@@ -77,6 +106,6 @@ def test_visible_gather_world_size_2_gloo(tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, 5000, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, 50_000, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert (tmp_path / f"rank{r}.ok").read_text() == "1"

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "zn_scene_set_bounds": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_size_t]),
     "zn_scene_set_parents": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
     "zn_scene_set_camera": (C.c_int, [vp, vp, vp]),
+    "zn_scene_bind_visible_output": (C.c_int, [vp, vp, C.c_uint32, vp]),
     "zn_scene_set_index_base": (C.c_int, [vp, C.c_uint32]),
     "zn_scene_update": (C.c_int, [vp]),
     "zn_scene_visible_count": (C.c_int, [vp, c_u32_p]),

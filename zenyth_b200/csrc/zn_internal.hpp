@@ -52,6 +52,7 @@ struct zn_level {
 	uint32_t begin = 0, end = 0;   // entity range
 	uint32_t tile_base = 0;        // first global tile id of this level
 	uint32_t tiles = 0;
+	uint32_t ticket_base = 0;      // tickets this level's counter has handed out in earlier frames
 	CUtensorMap tm_world, tm_mvp;  // extent clipped to `end` rows
 };
 
@@ -73,13 +74,16 @@ struct zn_scene {
 	// outputs
 	float* world = nullptr;        // [E][16]
 	float* mvp = nullptr;          // [E][16]
-	uint32_t* visible = nullptr;   // [E]
+	uint32_t* visible = nullptr;       // [E] where the emit kernel writes (own buffer or a bound one)
 	uint32_t* visible_count = nullptr; // [1] device
+	uint32_t* visible_own = nullptr;
+	uint32_t* visible_count_own = nullptr;
 	uint32_t* tile_mask = nullptr;         // [tiles][8] visibility bits of the tile
 	uint32_t* tile_first_entity = nullptr; // [tiles]
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
 	uint32_t* chunk_total = nullptr;       // [chunks] visible count per chunk; zero between frames
 	uint32_t* done_counter = nullptr;      // [1] emit CTAs finished this frame
+	uint32_t* level_ticket = nullptr;      // [levels] monotonically increasing tile tickets, one counter per level
 	uint32_t* host_count = nullptr;      // pinned [1]
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events; // [levels+2]

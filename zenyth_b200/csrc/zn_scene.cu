@@ -51,11 +51,13 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
                    const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
                    const uint2* __restrict__ tile_prange, const float* __restrict__ world_rd,
                    uint32_t begin, uint32_t end, uint32_t tile_base, uint32_t tiles,
-                   uint32_t* __restrict__ tile_mask, uint32_t* __restrict__ chunk_total) {
+                   uint32_t* __restrict__ tile_mask, uint32_t* __restrict__ chunk_total,
+                   uint32_t* __restrict__ ticket, uint32_t ticket_base) {
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ uint64_t s_full;
 	__shared__ uint2 s_meta;
 	__shared__ uint32_t s_mask[kWarpsPerTile];
+	__shared__ uint32_t s_tile[2];   // level-relative tile of iteration n (slot n&1) and n+1
 
 	// 1024-byte aligned tiles (the swizzle pattern is a function of the shared address bits)
 	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -89,12 +91,18 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		prefetch_tensormap(&tm_world);
 		prefetch_tensormap(&tm_mvp);
 		grid_dep_launch();          // the next level's kernel may start its own prologue now
-		issue_loads(blockIdx.x, true);
+		// Tiles are claimed dynamically (one atomic ticket per tile): a CTA that starts late — e.g.
+		// while a collective's kernel holds part of the SMs — simply takes fewer tiles.  The grid is
+		// never larger than the tile count, so every CTA gets at least one tile.
+		const uint32_t tl0 = atomicAdd(ticket, 1u) - ticket_base;
+		s_tile[0] = tl0;
+		if (tl0 < tiles) issue_loads(tl0, true);
 	}
 	__syncthreads();
 
-	uint32_t n = 0;
-	for (uint32_t tl = blockIdx.x; tl < tiles; tl += gridDim.x, ++n) {
+	for (uint32_t n = 0;; ++n) {
+		const uint32_t tl = s_tile[n & 1u];
+		if (tl >= tiles) break;
 		// ---- tile n: shared memory -> registers ------------------------------------------------
 		mbar_wait(&s_full, n & 1u);
 		float v[15];
@@ -121,7 +129,11 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		__syncthreads();                    // input stage consumed by everyone; out tile free
 
 		// ---- prefetch tile n+1 while tile n is computed ------------------------------------------
-		if (t == 0 && tl + gridDim.x < tiles) issue_loads(tl + gridDim.x, false);
+		if (t == 0) {
+			const uint32_t next = atomicAdd(ticket, 1u) - ticket_base;
+			s_tile[(n + 1u) & 1u] = next;   // read by everyone after the barrier below
+			if (next < tiles) issue_loads(next, false);
+		}
 
 		// ---- tile n: maths in registers ----------------------------------------------------------
 		const Affine local = local_trs(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
@@ -426,10 +438,14 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	ZN_TRY(cudaMalloc(&s->tile_prange, size_t(s->tile_count) * sizeof(uint2)));
 	ZN_TRY(cudaMalloc(&s->world, size_t(E) * 64));
 	ZN_TRY(cudaMalloc(&s->mvp, size_t(E) * 64));
-	ZN_TRY(cudaMalloc(&s->visible, size_t(E) * 4));
-	ZN_TRY(cudaMalloc(&s->visible_count, 4));
+	ZN_TRY(cudaMalloc(&s->visible_own, size_t(E) * 4));
+	ZN_TRY(cudaMalloc(&s->visible_count_own, 4));
+	s->visible = s->visible_own;
+	s->visible_count = s->visible_count_own;
 	ZN_TRY(cudaMalloc(&s->chunk_total, size_t(s->chunk_count) * 4));
 	ZN_TRY(cudaMalloc(&s->done_counter, 4));
+	ZN_TRY(cudaMalloc(&s->level_ticket, s->levels.size() * 4));
+	ZN_TRY(cudaMemsetAsync(s->level_ticket, 0, s->levels.size() * 4, ctx->stream));
 	ZN_TRY(cudaMalloc(&s->tile_mask, size_t(s->tile_count) * kWarpsPerTile * 4));
 	ZN_TRY(cudaMalloc(&s->tile_first_entity, size_t(s->tile_count) * 4));
 	ZN_TRY(cudaHostAlloc(&s->host_count, 4, cudaHostAllocDefault));
@@ -455,8 +471,8 @@ int zn_scene_destroy(zn_scene* s) {
 	if (!s) return ZN_OK;
 	cudaSetDevice(s->ctx->device);
 	cudaStreamSynchronize(s->ctx->stream);
-	cudaFree(s->blocks); cudaFree(s->tile_prange); cudaFree(s->world); cudaFree(s->mvp); cudaFree(s->visible);
-	cudaFree(s->visible_count); cudaFree(s->chunk_total); cudaFree(s->done_counter); cudaFree(s->tile_mask); cudaFree(s->tile_first_entity);
+	cudaFree(s->blocks); cudaFree(s->tile_prange); cudaFree(s->world); cudaFree(s->mvp); cudaFree(s->visible_own);
+	cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->done_counter); cudaFree(s->level_ticket); cudaFree(s->tile_mask); cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
 	for (auto e : s->prof_events) cudaEventDestroy(e);
 	delete s;
@@ -536,6 +552,20 @@ int zn_scene_set_camera(zn_scene* s, const float view[16], const float proj[16])
 	return ZN_OK;
 }
 
+int zn_scene_bind_visible_output(zn_scene* s, void* visible_dev, uint32_t capacity, void* visible_count_dev) {
+	ZN_REQUIRE(s, "zn_scene_bind_visible_output: scene is NULL");
+	if (!visible_dev && !visible_count_dev) {
+		s->visible = s->visible_own;
+		s->visible_count = s->visible_count_own;
+		return ZN_OK;
+	}
+	ZN_REQUIRE(visible_dev && visible_count_dev, "zn_scene_bind_visible_output: pass both pointers, or both NULL to restore the internal buffers");
+	ZN_REQUIRE(capacity >= s->entity_count, "zn_scene_bind_visible_output: capacity %u < entity_count %u", capacity, s->entity_count);
+	s->visible = static_cast<uint32_t*>(visible_dev);
+	s->visible_count = static_cast<uint32_t*>(visible_count_dev);
+	return ZN_OK;
+}
+
 int zn_scene_set_index_base(zn_scene* s, uint32_t index_base) {
 	ZN_REQUIRE(s, "zn_scene_set_index_base: scene is NULL");
 	s->index_base = index_base;
@@ -569,18 +599,22 @@ int zn_scene_update(zn_scene* s) {
 	cfg.stream = ctx->stream;
 	cfg.attrs = &pdl;
 	for (size_t l = 0; l < s->levels.size(); ++l) {
-		const zn_level& lv = s->levels[l];
-		cfg.gridDim = dim3(std::min<uint32_t>(lv.tiles, uint32_t(s->max_ctas)));
+		zn_level& lv = s->levels[l];
+		const uint32_t grid = std::min<uint32_t>(lv.tiles, uint32_t(s->max_ctas));
+		cfg.gridDim = dim3(grid);
 		cfg.numAttrs = (l == 0 || prof) ? 0 : 1;
 		if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[l], ctx->stream));
+		uint32_t* ticket = s->level_ticket + l;   // one counter per level: PDL lets consecutive levels overlap
 		if (l == 0)
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<false>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           s->tile_mask, s->chunk_total));
+			                           s->tile_mask, s->chunk_total, ticket, lv.ticket_base));
 		else
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<true>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           s->tile_mask, s->chunk_total));
+			                           s->tile_mask, s->chunk_total, ticket, lv.ticket_base));
+		// every tile takes one ticket and every CTA one more (the draw that tells it to stop)
+		lv.ticket_base += lv.tiles + grid;
 	}
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size()], ctx->stream));
 	cfg.gridDim = dim3(s->chunk_count);

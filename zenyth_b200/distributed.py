@@ -8,7 +8,7 @@ does no arithmetic of the path.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 
 def shard_scenes(num_scenes: int, world_size: int, rank: int) -> List[int]:
@@ -34,7 +34,7 @@ def scene_index_bases(entity_counts: Sequence[int]) -> List[int]:
 
 
 class VisibleGather:
-    """All-gather of variable-length visible lists.
+    """Blocking all-gather of variable-length visible lists.
 
     gather(visible, count) -> (counts, lists): `visible` is this rank's device-resident index buffer
     (capacity entries, first `count` valid), `count` a 1-element tensor on the same device.  Step 1
@@ -68,3 +68,102 @@ class VisibleGather:
         every rank's index base is the sum of the entity counts before it)."""
         import torch
         return torch.cat([lists[r, : counts[r]] for r in range(len(counts))])
+
+
+class VisibleExchange:
+    """Pipelined all-gather of visible lists: the exchange of frame k runs on the collective's own
+    stream while frame k+1 is computed ("overlapped with the gather on a second
+    stream").
+
+    Per slot (two by default) it owns this rank's list/count buffers — the scene writes into them
+    directly (zn_scene_bind_visible_output) — and the gathered buffers.  Protocol per frame k,
+    slot = k % slots:
+
+        ex.acquire(slot)      # frame k-slots' exchange is complete; its result may be collected
+        scene.BindVisibleOutput(ex.local_ptr(slot), capacity, ex.count_ptr(slot)); scene.Update()
+        ex.launch(slot)       # asynchronous: counts, then lists padded to a size all ranks agree on
+
+    The list all-gather needs a size known on the host.  Reading this frame's counts would stall the
+    GPU, so the size is the largest count of the most recently COLLECTED frame plus headroom (identical on all
+    ranks, because every rank sees the same gathered counts).  collect() checks the real counts; if
+    a list outgrew the guess the frame is re-gathered synchronously, so results are always exact.
+    """
+
+    def __init__(self, capacity: int, world_size: int, device, dtype, slots: int = 2, headroom: float = 0.02, group=None):
+        import torch
+        self.world_size, self.capacity, self.slots, self.headroom, self.group = world_size, int(capacity), slots, headroom, group
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.local = [torch.zeros(self.capacity, dtype=dtype, device=device) for _ in range(slots)]
+        self.local_count = [torch.zeros(1, dtype=dtype, device=device) for _ in range(slots)]
+        self.counts = [torch.zeros(world_size, dtype=dtype, device=device) for _ in range(slots)]
+        self.gathered = [torch.empty(world_size * self.capacity, dtype=dtype, device=device) for _ in range(slots)]
+        self.pending: List[Optional[tuple]] = [None] * slots
+        self.guess: Optional[int] = None
+        self.regathers = 0
+        if self.cuda:
+            # counts travel to the host on a side stream, so reading them never waits on compute
+            self.side = torch.cuda.Stream(self.device)
+            self.done = [torch.cuda.Event() for _ in range(slots)]
+            self.host_counts = [torch.zeros(world_size, dtype=dtype).pin_memory() for _ in range(slots)]
+
+    def local_ptr(self, slot: int) -> int:
+        return self.local[slot].data_ptr()
+
+    def count_ptr(self, slot: int) -> int:
+        return self.local_count[slot].data_ptr()
+
+    def _padded(self, n: int) -> int:
+        n = int(n * (1.0 + self.headroom)) + 1024
+        return max(1, min(self.capacity, (n + 1023) // 1024 * 1024))
+
+    def launch(self, slot: int) -> None:
+        import torch
+        import torch.distributed as dist
+        assert self.pending[slot] is None, "slot still holds an uncollected frame"
+        w1 = dist.all_gather_into_tensor(self.counts[slot], self.local_count[slot], group=self.group, async_op=True)
+        if self.guess is None:
+            w1.wait()
+            self.guess = self._padded(max(int(c) for c in self.counts[slot].tolist()))   # first frame only: a host sync
+        m = self.guess
+        out = self.gathered[slot][: self.world_size * m]
+        w2 = dist.all_gather_into_tensor(out, self.local[slot][:m], group=self.group, async_op=True)
+        if self.cuda:
+            with torch.cuda.stream(self.side):
+                w1.wait()
+                w2.wait()
+                self.host_counts[slot].copy_(self.counts[slot], non_blocking=True)
+                self.done[slot].record(self.side)
+        self.pending[slot] = (w1, w2, m)
+
+    def collect(self, slot: int):
+        """Result of the frame last launched on `slot`: (counts, lists[world, m]) or None."""
+        import torch
+        import torch.distributed as dist
+        if self.pending[slot] is None:
+            return None
+        w1, w2, m = self.pending[slot]
+        if self.cuda:
+            self.done[slot].synchronize()                              # host: that exchange has landed
+            torch.cuda.current_stream(self.device).wait_event(self.done[slot])   # compute stream may reuse the slot
+            counts = [int(c) for c in self.host_counts[slot].tolist()]
+        else:
+            w1.wait()
+            w2.wait()
+            counts = [int(c) for c in self.counts[slot].tolist()]
+        need = max(max(counts), 1)
+        if need > m:   # a list outgrew the guess: redo this frame at the right size (rare, exact)
+            self.regathers += 1
+            m = self._padded(need)
+            out = self.gathered[slot][: self.world_size * m]
+            dist.all_gather_into_tensor(out, self.local[slot][:m], group=self.group)
+        self.guess = self._padded(need)
+        self.pending[slot] = None
+        return counts, self.gathered[slot][: self.world_size * m].view(self.world_size, m)
+
+    def acquire(self, slot: int):
+        """Make `slot` reusable; returns the collected result of its previous frame (or None)."""
+        return self.collect(slot)
+
+    def drain(self):
+        return [self.collect(s) for s in range(self.slots)]

@@ -210,6 +210,10 @@ class Scene:
     def SetCamera(self, camera: Camera) -> None:
         check(self._lib.zn_scene_set_camera(self._h, _p(camera.view), _p(camera.proj)))
 
+    def BindVisibleOutput(self, visible_ptr: int | None, capacity: int = 0, count_ptr: int | None = None) -> None:
+        """Redirect the visible list / count into caller-owned device memory (raw device pointers)."""
+        check(self._lib.zn_scene_bind_visible_output(self._h, C.c_void_p(visible_ptr or 0), capacity, C.c_void_p(count_ptr or 0)))
+
     def SetIndexBase(self, base: int) -> None:
         check(self._lib.zn_scene_set_index_base(self._h, base))
 
