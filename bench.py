@@ -235,29 +235,47 @@ def run_ours(args) -> None:
     launches_per_update = scene.LaunchesPerUpdate()
 
     frame_no = [0]
-    if distributed:
-        # The one exchange of the path: all-gather the visible counts, then the
+    use_lists = distributed and args.exchange == "lists"
+    use_records = distributed and args.exchange == "records"
+    if use_lists:
+        # The exchange of the path as SURVEY §8e words it: all-gather the visible counts, then the
         # compacted index lists.  Double-buffered: the scene writes frame k's list straight into
         # slot k%2 of the exchange, whose NCCL all-gathers run on the collective's stream while
         # frame k+1 is computed; a slot is collected (checked, exact) before it is reused.
         from zenyth_b200.distributed import VisibleExchange
         exchange = VisibleExchange(E, world_size, dev, torch.int32, slots=2)
+    if use_records:
+        # Same result, 1 bit per entity on the wire: all-gather the fixed-size visibility records,
+        # every rank expands all of them into the ordered lists (zenyth_b200.distributed.RecordExchange).
+        from zenyth_b200.distributed import RecordExchange
+        exchange = RecordExchange(bufs.visibility_record_words, E, world_size, dev, torch.int32, slots=2)
+        index_bases = np.asarray([(r * E) % 2 ** 32 for r in range(world_size)], np.uint32)
 
     def step():
-        if distributed:
-            slot = frame_no[0] % 2
+        slot = frame_no[0] % 2
+        if use_lists:
             exchange.acquire(slot)
             scene.BindVisibleOutput(exchange.local_ptr(slot), E, exchange.count_ptr(slot))
             scene.Update()
             exchange.launch(slot)
+        elif use_records:
+            scene.BindVisibilityRecord(exchange.record_ptr(slot))
+            scene.Update()
+            exchange.launch(slot)                      # all-gather of frame k: overlaps what follows
+            if exchange.ready(1 - slot):               # frame k-1 has arrived: derive every rank's list
+                exchange.expand(scene, 1 - slot, index_bases)
         else:
             scene.Update()
         frame_no[0] += 1
 
     def finish():
         """All frames issued so far are complete, including their exchanges."""
-        if distributed:
+        if use_lists:
             exchange.drain()
+        if use_records:
+            for slot in ((frame_no[0] - 2) % 2, (frame_no[0] - 1) % 2):
+                if exchange.ready(slot):
+                    exchange.expand(scene, slot, index_bases)
 
     def barrier():
         if distributed:
@@ -268,10 +286,13 @@ def run_ours(args) -> None:
         step()
     finish()
     barrier()
-    if distributed:
+    if use_lists:
         scene.BindVisibleOutput(None)
         scene.Update()
     visible = scene.VisibleCount()
+    if use_records:   # every rank derived the same lists: check the count of this rank's own
+        counts, _ = exchange.result()
+        assert counts[rank] == visible, (counts, visible)
 
     gpu_id = str(torch.cuda.get_device_properties(dev).uuid)
     if not gpu_id.startswith("GPU-"):
@@ -286,8 +307,10 @@ def run_ours(args) -> None:
     stop.record(stream)
     barrier()
     clocks = sampler.stop()
-    if distributed:
+    if use_lists:
         scene.BindVisibleOutput(None)
+    if use_records:
+        scene.BindVisibilityRecord(None)
     ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -358,9 +381,15 @@ def run_ours(args) -> None:
                        "visible_fraction": visible / E,
                        "l2": "inputs 1.07 GB + outputs 2.15 GB per step >> 126 MB L2, no flush needed" if E > 4_000_000
                              else "footprint ~%d MB vs 126 MB L2" % (E * 192 // 1_000_000),
-                       "collective": ("NCCL all_gather of visible counts + index lists every step, double-buffered: the exchange of "
-                                      "frame k overlaps the update of frame k+1; the timed region ends after the last exchange; "
-                                      f"re-gathers after a size misprediction: {exchange.regathers}") if distributed else "none (1 GPU)"},
+                       "collective": (
+                           ("NCCL all_gather of visible counts + index lists every step, double-buffered: the exchange of "
+                            "frame k overlaps the update of frame k+1; the timed region ends after the last exchange; "
+                            f"re-gathers after a size misprediction: {exchange.regathers}") if use_lists else
+                           ("NCCL all_gather of the fixed-size visibility records (per-chunk counts + 1 mask bit per entity) "
+                            "every step, double-buffered; every rank then expands all records into the ordered index lists + "
+                            "counts (identical to an all-gather of the lists, 27x fewer NVLink bytes); the timed region "
+                            "ends after the last expansion; --exchange lists runs the literal list all-gather") if use_records
+                           else "none (1 GPU)")},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -389,6 +418,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="h8geo16m")
+    ap.add_argument("--exchange", choices=["records", "lists"], default="records",
+                    help="N>1: all-gather visibility records and expand locally (default), or all-gather the index lists")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     args = ap.parse_args()

@@ -107,6 +107,22 @@ int zn_scene_set_camera(zn_scene* scene, const float view[16], const float proj[
  * frame k+1 is computed).  capacity (in indices) must be >= entity_count.  Both NULL restores the
  * scene's own buffers. */
 int zn_scene_bind_visible_output(zn_scene* scene, void* visible_dev, uint32_t capacity, void* visible_count_dev);
+/* Multi-GPU exchange at 1 bit per entity.  A frame's visible set also exists as a fixed-size
+ * "visibility record" (zn_scene_buffers.visibility_record).  Ranks all-gather the records (27x
+ * fewer bytes than the index lists at the bench's visible fraction, and a size known without
+ * reading the count) and every rank expands them into the same ordered index lists with
+ * zn_scene_expand_visible — the arithmetic of the local compaction, so the lists are identical
+ * to an all-gather of the lists themselves.
+ *   zn_scene_bind_visibility_record: subsequent updates write the record into caller-owned DEVICE
+ *     memory (>= visibility_record_words words; e.g. a slot of a double-buffered all-gather input).
+ *     NULL restores the scene's own buffer.
+ *   zn_scene_expand_visible: expands `record_count` (<= 64) records laid out `record_stride_words`
+ *     apart, of scenes with THIS scene's level layout, into lists_dev[r*list_stride ...] and
+ *     counts_dev[r]; index_bases[r] (host array, may be NULL) is added to record r's indices;
+ *     record `skip_index` is left out (-1: none).  Asynchronous on the context stream. */
+int zn_scene_bind_visibility_record(zn_scene* scene, void* record_dev);
+int zn_scene_expand_visible(zn_scene* scene, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
+                            int skip_index, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev);
 /* Added to every index written to the visible list (shard -> global numbering). */
 int zn_scene_set_index_base(zn_scene* scene, uint32_t index_base);
 
@@ -128,6 +144,9 @@ typedef struct zn_scene_buffers {
 	void* mvp;              /* float[E][16] */
 	void* visible;          /* uint32[E], first *visible_count entries valid, ascending */
 	void* visible_count;    /* uint32[1] */
+	void* visibility_record;          /* uint32[visibility_record_words]: the frame's visible set at 1 bit per
+	                                     entity — per-chunk counts, then 8 mask words per 256-entity tile */
+	uint32_t visibility_record_words;
 	uint32_t entity_count;
 } zn_scene_buffers;
 int zn_scene_device_buffers(zn_scene* scene, zn_scene_buffers* out);

@@ -156,3 +156,45 @@ def test_errors_are_loud(gpu_ctx):
     with pytest.raises(zn.ZenythError):
         sc.World(first=10, count=10)
     sc.Close()
+
+
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+
+
+def test_visibility_record_expands_to_the_same_list(oracle, gpu_ctx):
+    """The 1-bit-per-entity record that multi-GPU runs exchange reproduces the compacted list."""
+    import torch
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 5)
+    E = sum(sizes)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    view, proj = camera(oracle)
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    # the record may live in caller memory (a slot of an all-gather input)
+    words = sc.DeviceBuffers().visibility_record_words
+    rec = torch.zeros(3 * words, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    sc.BindVisibilityRecord(rec.data_ptr() + 4 * words)          # middle slot
+    sc.Update()
+    vis = sc.Visible()
+    assert np.array_equal(vis, oracle.scene_update(arrays, view, proj)["visible"])
+    rec[:words] = rec[words:2 * words]                           # three "ranks" with the same record
+    rec[2 * words:] = rec[words:2 * words]
+    lists = torch.full((3 * E,), -1, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(3, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    sc.ExpandVisible(rec.data_ptr(), 3, words, lists.data_ptr(), E, counts.data_ptr(), index_bases=[0, 1000, 5], skip_index=2)
+    gpu_ctx.Sync()
+    assert counts.tolist() == [vis.size, vis.size, 0]
+    got = lists.view(3, E).cpu().numpy()
+    assert np.array_equal(got[0, :vis.size], vis.astype(np.int32))
+    assert np.array_equal(got[1, :vis.size], vis.astype(np.int32) + 1000)
+    assert np.all(got[2] == -1)                                  # skipped record untouched
+    sc.BindVisibilityRecord(None)
+    sc.Update()
+    assert np.array_equal(sc.Visible(), vis)
+    sc.Close()

@@ -29,7 +29,8 @@ class SceneDesc(C.Structure):
 
 
 class SceneBuffers(C.Structure):
-    _fields_ = [("world", vp), ("mvp", vp), ("visible", vp), ("visible_count", vp), ("entity_count", C.c_uint32)]
+    _fields_ = [("world", vp), ("mvp", vp), ("visible", vp), ("visible_count", vp), ("visibility_record", vp),
+                ("visibility_record_words", C.c_uint32), ("entity_count", C.c_uint32)]
 
 
 class FrameHostIO(C.Structure):
@@ -71,6 +72,8 @@ PROTOTYPES = {
     "zn_scene_set_parents": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
     "zn_scene_set_camera": (C.c_int, [vp, vp, vp]),
     "zn_scene_bind_visible_output": (C.c_int, [vp, vp, C.c_uint32, vp]),
+    "zn_scene_bind_visibility_record": (C.c_int, [vp, vp]),
+    "zn_scene_expand_visible": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, C.c_uint32, vp]),
     "zn_scene_set_index_base": (C.c_int, [vp, C.c_uint32]),
     "zn_scene_update": (C.c_int, [vp]),
     "zn_scene_visible_count": (C.c_int, [vp, c_u32_p]),

@@ -78,7 +78,10 @@ struct zn_scene {
 	uint32_t* visible_count = nullptr; // [1] device
 	uint32_t* visible_own = nullptr;
 	uint32_t* visible_count_own = nullptr;
-	uint32_t* tile_mask = nullptr;         // [tiles][8] visibility bits of the tile
+	// visibility record of a frame: [chunks] per-chunk visible counts, then [tiles][8] mask words
+	uint32_t* record = nullptr;            // where the kernels write (own buffer or a bound one)
+	uint32_t* record_own = nullptr;
+	uint32_t record_words = 0;
 	uint32_t* tile_first_entity = nullptr; // [tiles]
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
 	uint32_t* chunk_total = nullptr;       // [chunks] visible count per chunk; zero between frames

@@ -178,32 +178,27 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 	if (t == 0) bulk_wait_read_all();
 }
 
-// Ordered visible list, one pass over the 256-bit tile masks.  The level kernels have already
-// accumulated every chunk's visible count (chunk_total, one atomicAdd per tile), so an emit CTA
-// gets its base offset by summing the totals of the chunks before it — a few KiB of L2 reads, no
-// serial dependency between CTAs — then scatters its set bits in ascending order.  The last CTA to
-// finish re-zeroes the totals for the next frame.
-__global__ void __launch_bounds__(256)
-emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __restrict__ tile_first_entity,
-                    uint32_t tiles, uint32_t chunks, uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ done_counter,
-                    uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
+// One chunk (32 tiles = 8192 entities) of an ordered visible list: `totals` holds every chunk's
+// visible count, `masks` the 256-bit tile masks.  The CTA gets its base offset by summing the
+// totals of the chunks before it — a few KiB of L2 reads, no serial dependency between CTAs —
+// then scatters its set bits in ascending order.  Returns this chunk's own count (in every thread).
+__device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ totals, const uint32_t* __restrict__ masks,
+                                               const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t chunks,
+                                               uint32_t chunk, uint32_t index_base, uint32_t* __restrict__ visible,
+                                               uint32_t* __restrict__ visible_count) {
 	__shared__ uint32_t s_part[8];
 	__shared__ uint32_t s_warp_excl[8];
-	__shared__ uint32_t s_base;
-	__shared__ uint32_t s_last;
+	__shared__ uint32_t s_base, s_total;
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	const uint32_t chunk = blockIdx.x;
-	grid_dep_wait();   // masks and totals of every level are complete and visible
 
-	// base = sum of the totals of all earlier chunks
 	uint32_t acc = 0;
-	for (uint32_t j = t; j < chunk; j += 256) acc += __ldcg(chunk_total + j);
+	for (uint32_t j = t; j < chunk; j += 256) acc += __ldcg(totals + j);
 	acc = __reduce_add_sync(0xffffffffu, acc);
 	if (lane == 0) s_part[warp] = acc;
 
 	// thread t owns mask word t of the chunk: tile chunk*32 + t/8, word t%8
 	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
-	const uint32_t word = (tile < tiles) ? __ldcg(tile_mask + size_t(tile) * kWarpsPerTile + (t & 7)) : 0u;
+	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (t & 7)) : 0u;
 	const uint32_t cnt = __popc(word);
 	uint32_t incl = cnt;
 #pragma unroll
@@ -226,6 +221,7 @@ emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __re
 		if (lane < 8) s_warp_excl[lane] = winc - wt;
 		if (lane == 0) {
 			s_base = base;
+			s_total = total;
 			if (chunk == chunks - 1) *visible_count = base + total;
 		}
 	}
@@ -242,8 +238,26 @@ emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __re
 		const uint32_t f = __shfl_sync(0xffffffffu, first, w);
 		if ((mw >> lane) & 1u) visible[off + __popc(mw & lt)] = f + lane;
 	}
+	return s_total;
+}
 
-	// last CTA out re-zeroes the totals (every CTA has read them before it bumps the counter)
+// K3: the frame's own ordered visible list.  The level kernels accumulated every chunk's visible
+// count (chunk_total, one atomicAdd per tile).  Each CTA also stores its chunk's count into the
+// frame's visibility record (record = [chunks totals][tiles x 8 mask words]) — the 1-bit-per-entity
+// form of the result that a multi-GPU exchange ships instead of the 32-bit-per-visible-entity
+// list.  The last CTA to finish re-zeroes the accumulators for the next frame.
+__global__ void __launch_bounds__(256)
+emit_visible_kernel(uint32_t* __restrict__ record, const uint32_t* __restrict__ tile_first_entity,
+                    uint32_t tiles, uint32_t chunks, uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ done_counter,
+                    uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
+	__shared__ uint32_t s_last;
+	const int t = threadIdx.x;
+	const uint32_t chunk = blockIdx.x;
+	grid_dep_wait();   // masks and totals of every level are complete and visible
+	const uint32_t total = emit_chunk(chunk_total, record + chunks, tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count);
+	if (t == 0) record[chunk] = total;
+
+	// last CTA out re-zeroes the accumulators (every CTA has read them before it bumps the counter)
 	__syncthreads();
 	if (t == 0) {
 		__threadfence();
@@ -254,6 +268,22 @@ emit_visible_kernel(const uint32_t* __restrict__ tile_mask, const uint32_t* __re
 		for (uint32_t j = t; j < chunks; j += 256) chunk_total[j] = 0u;
 		if (t == 0) *done_counter = 0u;
 	}
+}
+
+// Expands `gridDim.y` visibility records (this rank's and its peers', as all-gathered) into their
+// ordered index lists: lists[r*list_stride ...], counts[r].  Same arithmetic as emit_visible_kernel,
+// so every rank derives bit-identical lists from the 27x smaller records.
+struct ExpandBases {
+	uint32_t base[64];
+};
+__global__ void __launch_bounds__(256)
+expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
+                      uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, int skip,
+                      uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ counts) {
+	const uint32_t r = blockIdx.y;
+	if (int(r) == skip) return;
+	const uint32_t* rec = records + size_t(r) * record_stride;
+	emit_chunk(rec, rec + chunks, tile_first_entity, tiles, chunks, blockIdx.x, bases.base[r], lists + size_t(r) * list_stride, counts + r);
 }
 
 // {first parent, parent count} of every tile: one warp per tile over the parent row of its block.
@@ -446,7 +476,10 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	ZN_TRY(cudaMalloc(&s->done_counter, 4));
 	ZN_TRY(cudaMalloc(&s->level_ticket, s->levels.size() * 4));
 	ZN_TRY(cudaMemsetAsync(s->level_ticket, 0, s->levels.size() * 4, ctx->stream));
-	ZN_TRY(cudaMalloc(&s->tile_mask, size_t(s->tile_count) * kWarpsPerTile * 4));
+	s->record_words = s->chunk_count + s->tile_count * kWarpsPerTile;
+	ZN_TRY(cudaMalloc(&s->record_own, size_t(s->record_words) * 4));
+	ZN_TRY(cudaMemsetAsync(s->record_own, 0, size_t(s->record_words) * 4, ctx->stream));
+	s->record = s->record_own;
 	ZN_TRY(cudaMalloc(&s->tile_first_entity, size_t(s->tile_count) * 4));
 	ZN_TRY(cudaHostAlloc(&s->host_count, 4, cudaHostAllocDefault));
 	ZN_TRY(cudaMemsetAsync(s->blocks, 0, size_t(s->tile_count) * kBlockWords * 4, ctx->stream));
@@ -472,7 +505,7 @@ int zn_scene_destroy(zn_scene* s) {
 	cudaSetDevice(s->ctx->device);
 	cudaStreamSynchronize(s->ctx->stream);
 	cudaFree(s->blocks); cudaFree(s->tile_prange); cudaFree(s->world); cudaFree(s->mvp); cudaFree(s->visible_own);
-	cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->done_counter); cudaFree(s->level_ticket); cudaFree(s->tile_mask); cudaFree(s->tile_first_entity);
+	cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->done_counter); cudaFree(s->level_ticket); cudaFree(s->record_own); cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
 	for (auto e : s->prof_events) cudaEventDestroy(e);
 	delete s;
@@ -566,6 +599,28 @@ int zn_scene_bind_visible_output(zn_scene* s, void* visible_dev, uint32_t capaci
 	return ZN_OK;
 }
 
+int zn_scene_bind_visibility_record(zn_scene* s, void* record_dev) {
+	ZN_REQUIRE(s, "zn_scene_bind_visibility_record: scene is NULL");
+	s->record = record_dev ? static_cast<uint32_t*>(record_dev) : s->record_own;
+	return ZN_OK;
+}
+
+int zn_scene_expand_visible(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
+                            const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev) {
+	ZN_REQUIRE(s && records_dev && lists_dev && counts_dev, "zn_scene_expand_visible: NULL argument");
+	ZN_REQUIRE(record_count >= 1 && record_count <= 64, "zn_scene_expand_visible: record_count %u must be in [1, 64]", record_count);
+	ZN_REQUIRE(record_stride_words >= s->record_words, "zn_scene_expand_visible: record stride %u < record size %u words", record_stride_words, s->record_words);
+	ZN_REQUIRE(list_stride >= s->entity_count, "zn_scene_expand_visible: list stride %u < entity_count %u", list_stride, s->entity_count);
+	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	ExpandBases bases;
+	for (uint32_t r = 0; r < 64; ++r) bases.base[r] = (index_bases && r < record_count) ? index_bases[r] : 0u;
+	expand_visible_kernel<<<dim3(s->chunk_count, record_count), 256, 0, s->ctx->stream>>>(
+		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, skip_index,
+		static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev));
+	ZN_CUDA(cudaGetLastError());
+	return ZN_OK;
+}
+
 int zn_scene_set_index_base(zn_scene* s, uint32_t index_base) {
 	ZN_REQUIRE(s, "zn_scene_set_index_base: scene is NULL");
 	s->index_base = index_base;
@@ -608,11 +663,11 @@ int zn_scene_update(zn_scene* s) {
 		if (l == 0)
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<false>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           s->tile_mask, s->chunk_total, ticket, lv.ticket_base));
+			                           s->record + s->chunk_count, s->chunk_total, ticket, lv.ticket_base));
 		else
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<true>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           s->tile_mask, s->chunk_total, ticket, lv.ticket_base));
+			                           s->record + s->chunk_count, s->chunk_total, ticket, lv.ticket_base));
 		// every tile takes one ticket and every CTA one more (the draw that tells it to stop)
 		lv.ticket_base += lv.tiles + grid;
 	}
@@ -621,7 +676,7 @@ int zn_scene_update(zn_scene* s) {
 	cfg.blockDim = dim3(256);
 	cfg.dynamicSmemBytes = 0;
 	cfg.numAttrs = prof ? 0 : 1;
-	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, (const uint32_t*)s->tile_mask, (const uint32_t*)s->tile_first_entity,
+	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, s->record, (const uint32_t*)s->tile_first_entity,
 	                           s->tile_count, s->chunk_count, s->chunk_total, s->done_counter, s->index_base, s->visible, s->visible_count));
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
 	return ZN_OK;
@@ -723,6 +778,8 @@ int zn_scene_device_buffers(zn_scene* s, zn_scene_buffers* out) {
 	out->mvp = s->mvp;
 	out->visible = s->visible;
 	out->visible_count = s->visible_count;
+	out->visibility_record = s->record;
+	out->visibility_record_words = s->record_words;
 	out->entity_count = s->entity_count;
 	return ZN_OK;
 }

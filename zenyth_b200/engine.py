@@ -214,6 +214,17 @@ class Scene:
         """Redirect the visible list / count into caller-owned device memory (raw device pointers)."""
         check(self._lib.zn_scene_bind_visible_output(self._h, C.c_void_p(visible_ptr or 0), capacity, C.c_void_p(count_ptr or 0)))
 
+    def BindVisibilityRecord(self, record_ptr: int | None) -> None:
+        """Subsequent updates write the frame's visibility record into caller-owned device memory."""
+        check(self._lib.zn_scene_bind_visibility_record(self._h, C.c_void_p(record_ptr or 0)))
+
+    def ExpandVisible(self, records_ptr: int, record_count: int, record_stride_words: int, lists_ptr: int, list_stride: int,
+                      counts_ptr: int, index_bases=None, skip_index: int = -1) -> None:
+        """Expand all-gathered visibility records into ordered index lists (zn_scene_expand_visible)."""
+        bases = None if index_bases is None else np.ascontiguousarray(index_bases, np.uint32)
+        check(self._lib.zn_scene_expand_visible(self._h, C.c_void_p(records_ptr), record_count, record_stride_words, skip_index,
+                                                _p(bases), C.c_void_p(lists_ptr), list_stride, C.c_void_p(counts_ptr)))
+
     def SetIndexBase(self, base: int) -> None:
         check(self._lib.zn_scene_set_index_base(self._h, base))
 
