@@ -84,8 +84,8 @@ struct zn_scene {
 	uint32_t record_words = 0;
 	uint32_t* tile_first_entity = nullptr; // [tiles]
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
-	uint32_t* chunk_total = nullptr;       // [chunks] visible count per chunk; zero between frames
-	uint32_t* done_counter = nullptr;      // [1] emit CTAs finished this frame
+	uint32_t* chunk_total = nullptr;       // [2][chunks] visible count per chunk, one set per frame parity
+	uint32_t frame_parity = 0;
 	uint32_t* level_ticket = nullptr;      // [levels] monotonically increasing tile tickets, one counter per level
 	uint32_t* host_count = nullptr;      // pinned [1]
 	bool profiling = false;

@@ -182,10 +182,18 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 // visible count, `masks` the 256-bit tile masks.  The CTA gets its base offset by summing the
 // totals of the chunks before it — a few KiB of L2 reads, no serial dependency between CTAs —
 // then scatters its set bits in ascending order.  Returns this chunk's own count (in every thread).
+// Visibility record of a frame (what a multi-GPU exchange ships, 1 bit per entity):
+//   [0, chunks)                  exclusive base of every chunk in the visible list
+//   [chunks]                     total visible count
+//   [chunks+1, chunks+1+8*chunks) exclusive offset of every 4-tile group within its chunk
+//   (padding to a multiple of 4 words)
+//   [header, header + 8*tiles)   the 256-bit tile masks
+__host__ __device__ inline uint32_t record_header_words(uint32_t chunks) { return (chunks * 9u + 1u + 3u) & ~3u; }
+
 __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ totals, const uint32_t* __restrict__ masks,
                                                const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t chunks,
                                                uint32_t chunk, uint32_t index_base, uint32_t* __restrict__ visible,
-                                               uint32_t* __restrict__ visible_count) {
+                                               uint32_t* __restrict__ visible_count, uint32_t* __restrict__ record_out) {
 	__shared__ uint32_t s_part[8];
 	__shared__ uint32_t s_warp_excl[8];
 	__shared__ uint32_t s_base, s_total;
@@ -218,25 +226,51 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 		}
 		const uint32_t base = __reduce_add_sync(0xffffffffu, (lane < 8) ? s_part[lane] : 0u);
 		const uint32_t total = __shfl_sync(0xffffffffu, winc, 7);
-		if (lane < 8) s_warp_excl[lane] = winc - wt;
+		if (lane < 8) {
+			s_warp_excl[lane] = winc - wt;
+			record_out[chunks + 1u + chunk * 8u + lane] = winc - wt;
+		}
 		if (lane == 0) {
 			s_base = base;
 			s_total = total;
-			if (chunk == chunks - 1) *visible_count = base + total;
+			record_out[chunk] = base;
+			if (chunk == chunks - 1) {
+				*visible_count = base + total;
+				record_out[chunks] = base + total;
+			}
 		}
 	}
 	__syncthreads();
 	const uint32_t my_off = s_base + s_warp_excl[warp] + incl - cnt;   // exclusive offset of this thread's word
-	const uint32_t first = (tile < tiles) ? tile_first_entity[tile] + index_base + (t & 7) * 32 : 0u;
-	// warp-cooperative scatter: word by word, lanes write the set bits in ascending order
+	// warp-cooperative scatter: a warp owns 32 words (4 tiles); every lane tests ITS bit of a word,
+	// so the stores of a word are one coalesced run in ascending order.  The words and offsets are
+	// staged in shared memory and fetched four at a time (one LDS.128 each, broadcast) — the loop
+	// is issue-bound, not bandwidth-bound, so instructions per word are what count.
+	__shared__ __align__(16) uint32_t s_word[256];
+	__shared__ __align__(16) uint32_t s_off[256];
+	__shared__ uint32_t s_first[kChunkTiles];
+	s_word[t] = word;
+	s_off[t] = my_off;
+	if ((t & 7) == 0) s_first[t >> 3] = (tile < tiles) ? tile_first_entity[tile] + index_base : 0u;
+	__syncwarp();
 	const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll 4
-	for (int w = 0; w < 32; ++w) {
-		const uint32_t mw = __shfl_sync(0xffffffffu, word, w);
-		if (mw == 0u) continue;
-		const uint32_t off = __shfl_sync(0xffffffffu, my_off, w);
-		const uint32_t f = __shfl_sync(0xffffffffu, first, w);
-		if ((mw >> lane) & 1u) visible[off + __popc(mw & lt)] = f + lane;
+	const uint4* w4 = reinterpret_cast<const uint4*>(s_word + warp * 32);
+	const uint4* o4 = reinterpret_cast<const uint4*>(s_off + warp * 32);
+#pragma unroll
+	for (int g = 0; g < 8; ++g) {   // words 4g..4g+3 belong to tile g/2 of this warp
+		const uint4 m = w4[g];
+		const uint4 o = o4[g];
+		const uint32_t f = s_first[warp * 4 + (g >> 1)] + (g & 1) * 128 + lane;
+		// a word is warp-uniform, so these branches never diverge: visibility is spatially coherent
+		// and most words are all-ones (one full 128-byte store) or zero (nothing to do)
+		auto put = [&](uint32_t mw, uint32_t off, uint32_t value) {
+			if (mw == 0xffffffffu) visible[off + lane] = value;
+			else if (mw != 0u && ((mw >> lane) & 1u)) visible[off + __popc(mw & lt)] = value;
+		};
+		put(m.x, o.x, f);
+		put(m.y, o.y, f + 32);
+		put(m.z, o.z, f + 64);
+		put(m.w, o.w, f + 96);
 	}
 	return s_total;
 }
@@ -245,29 +279,17 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 // count (chunk_total, one atomicAdd per tile).  Each CTA also stores its chunk's count into the
 // frame's visibility record (record = [chunks totals][tiles x 8 mask words]) — the 1-bit-per-entity
 // form of the result that a multi-GPU exchange ships instead of the 32-bit-per-visible-entity
-// list.  The last CTA to finish re-zeroes the accumulators for the next frame.
+// list.  The accumulators are double-buffered by frame parity: while reading this frame's set,
+// every CTA clears its own entry of the OTHER set (last read by the previous frame's emit), so the
+// next frame finds zeros without any cross-CTA handshake.
 __global__ void __launch_bounds__(256)
 emit_visible_kernel(uint32_t* __restrict__ record, const uint32_t* __restrict__ tile_first_entity,
-                    uint32_t tiles, uint32_t chunks, uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ done_counter,
+                    uint32_t tiles, uint32_t chunks, const uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ chunk_total_next,
                     uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
-	__shared__ uint32_t s_last;
-	const int t = threadIdx.x;
 	const uint32_t chunk = blockIdx.x;
 	grid_dep_wait();   // masks and totals of every level are complete and visible
-	const uint32_t total = emit_chunk(chunk_total, record + chunks, tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count);
-	if (t == 0) record[chunk] = total;
-
-	// last CTA out re-zeroes the accumulators (every CTA has read them before it bumps the counter)
-	__syncthreads();
-	if (t == 0) {
-		__threadfence();
-		s_last = (atomicAdd(done_counter, 1u) == chunks - 1u) ? 1u : 0u;
-	}
-	__syncthreads();
-	if (s_last) {
-		for (uint32_t j = t; j < chunks; j += 256) chunk_total[j] = 0u;
-		if (t == 0) *done_counter = 0u;
-	}
+	emit_chunk(chunk_total, record + record_header_words(chunks), tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count, record);
+	if (threadIdx.x == 0) chunk_total_next[chunk] = 0u;
 }
 
 // Expands `gridDim.y` visibility records (this rank's and its peers', as all-gathered) into their
@@ -276,14 +298,57 @@ emit_visible_kernel(uint32_t* __restrict__ record, const uint32_t* __restrict__ 
 struct ExpandBases {
 	uint32_t base[64];
 };
+// A record already carries every offset the owner computed (chunk bases, group offsets), so a warp
+// here is autonomous: 32 mask words (4 tiles) + two offsets in, a warp scan, the scatter out — no
+// shared-memory reduction, no block barrier.
 __global__ void __launch_bounds__(256)
 expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
                       uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, int skip,
                       uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ counts) {
+	__shared__ __align__(16) uint32_t s_word[256];
+	__shared__ __align__(16) uint32_t s_off[256];
+	__shared__ uint32_t s_first[kChunkTiles];
 	const uint32_t r = blockIdx.y;
 	if (int(r) == skip) return;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	const uint32_t* rec = records + size_t(r) * record_stride;
-	emit_chunk(rec, rec + chunks, tile_first_entity, tiles, chunks, blockIdx.x, bases.base[r], lists + size_t(r) * list_stride, counts + r);
+	const uint32_t* masks = rec + record_header_words(chunks);
+	uint32_t* visible = lists + size_t(r) * list_stride;
+	const uint32_t chunk = blockIdx.x;
+	const uint32_t group = chunk * 8u + warp;                 // 4 tiles = 32 mask words
+	const uint32_t tile = group * 4u + (lane >> 3);
+	if (tile - (lane >> 3) >= tiles) return;                  // whole group past the end (warp-uniform)
+	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
+	const uint32_t base = __ldcg(rec + chunk) + __ldcg(rec + chunks + 1u + group);
+	if (chunk == 0 && t == 0) counts[r] = __ldcg(rec + chunks);
+	const uint32_t cnt = __popc(word);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += y;
+	}
+	s_word[t] = word;
+	s_off[t] = base + incl - cnt;
+	if ((lane & 7) == 0) s_first[t >> 3] = (tile < tiles) ? tile_first_entity[tile] + bases.base[r] : 0u;
+	__syncwarp();
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint4* w4 = reinterpret_cast<const uint4*>(s_word + warp * 32);
+	const uint4* o4 = reinterpret_cast<const uint4*>(s_off + warp * 32);
+#pragma unroll
+	for (int g = 0; g < 8; ++g) {
+		const uint4 m = w4[g];
+		const uint4 o = o4[g];
+		const uint32_t f = s_first[warp * 4 + (g >> 1)] + (g & 1) * 128 + lane;
+		auto put = [&](uint32_t mw, uint32_t off, uint32_t value) {
+			if (mw == 0xffffffffu) visible[off + lane] = value;
+			else if (mw != 0u && ((mw >> lane) & 1u)) visible[off + __popc(mw & lt)] = value;
+		};
+		put(m.x, o.x, f);
+		put(m.y, o.y, f + 32);
+		put(m.z, o.z, f + 64);
+		put(m.w, o.w, f + 96);
+	}
 }
 
 // {first parent, parent count} of every tile: one warp per tile over the parent row of its block.
@@ -472,11 +537,10 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	ZN_TRY(cudaMalloc(&s->visible_count_own, 4));
 	s->visible = s->visible_own;
 	s->visible_count = s->visible_count_own;
-	ZN_TRY(cudaMalloc(&s->chunk_total, size_t(s->chunk_count) * 4));
-	ZN_TRY(cudaMalloc(&s->done_counter, 4));
+	ZN_TRY(cudaMalloc(&s->chunk_total, size_t(s->chunk_count) * 2 * 4));   // two sets, by frame parity
 	ZN_TRY(cudaMalloc(&s->level_ticket, s->levels.size() * 4));
 	ZN_TRY(cudaMemsetAsync(s->level_ticket, 0, s->levels.size() * 4, ctx->stream));
-	s->record_words = s->chunk_count + s->tile_count * kWarpsPerTile;
+	s->record_words = record_header_words(s->chunk_count) + s->tile_count * kWarpsPerTile;
 	ZN_TRY(cudaMalloc(&s->record_own, size_t(s->record_words) * 4));
 	ZN_TRY(cudaMemsetAsync(s->record_own, 0, size_t(s->record_words) * 4, ctx->stream));
 	s->record = s->record_own;
@@ -485,8 +549,7 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	ZN_TRY(cudaMemsetAsync(s->blocks, 0, size_t(s->tile_count) * kBlockWords * 4, ctx->stream));
 	init_parent_rows_kernel<<<(s->tile_count * kTile + 255) / 256, 256, 0, ctx->stream>>>(s->blocks, s->tile_count);
 	ZN_TRY(cudaGetLastError());
-	ZN_TRY(cudaMemsetAsync(s->chunk_total, 0, size_t(s->chunk_count) * 4, ctx->stream));
-	ZN_TRY(cudaMemsetAsync(s->done_counter, 0, 4, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(s->chunk_total, 0, size_t(s->chunk_count) * 2 * 4, ctx->stream));
 	ZN_TRY(cudaMemcpyAsync(s->tile_first_entity, tile_first.data(), tile_first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	ZN_TRY(cudaMemsetAsync(s->visible_count, 0, 4, ctx->stream));
 	ZN_TRY(cudaStreamSynchronize(ctx->stream));
@@ -505,7 +568,7 @@ int zn_scene_destroy(zn_scene* s) {
 	cudaSetDevice(s->ctx->device);
 	cudaStreamSynchronize(s->ctx->stream);
 	cudaFree(s->blocks); cudaFree(s->tile_prange); cudaFree(s->world); cudaFree(s->mvp); cudaFree(s->visible_own);
-	cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->done_counter); cudaFree(s->level_ticket); cudaFree(s->record_own); cudaFree(s->tile_first_entity);
+	cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->level_ticket); cudaFree(s->record_own); cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
 	for (auto e : s->prof_events) cudaEventDestroy(e);
 	delete s;
@@ -641,6 +704,9 @@ int zn_scene_update(zn_scene* s) {
 	std::memcpy(fc.vp, s->view_proj, sizeof(fc.vp));
 	std::memcpy(fc.planes, s->planes, sizeof(fc.planes));
 	const bool prof = s->profiling;
+	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
+	uint32_t* totals_next = s->chunk_total + size_t(s->frame_parity ^ 1u) * s->chunk_count;
+	s->frame_parity ^= 1u;
 	// Levels >= 1 and the emit kernel are launched with programmatic stream serialization: their
 	// prologue (and the first input-block load) overlaps the tail of the kernel before them; they
 	// call griddepcontrol.wait before touching anything that kernel wrote.  Level 0 is a normal
@@ -663,11 +729,11 @@ int zn_scene_update(zn_scene* s) {
 		if (l == 0)
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<false>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           s->record + s->chunk_count, s->chunk_total, ticket, lv.ticket_base));
+			                           s->record + record_header_words(s->chunk_count), totals, ticket, lv.ticket_base));
 		else
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<true>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           s->record + s->chunk_count, s->chunk_total, ticket, lv.ticket_base));
+			                           s->record + record_header_words(s->chunk_count), totals, ticket, lv.ticket_base));
 		// every tile takes one ticket and every CTA one more (the draw that tells it to stop)
 		lv.ticket_base += lv.tiles + grid;
 	}
@@ -677,7 +743,7 @@ int zn_scene_update(zn_scene* s) {
 	cfg.dynamicSmemBytes = 0;
 	cfg.numAttrs = prof ? 0 : 1;
 	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, s->record, (const uint32_t*)s->tile_first_entity,
-	                           s->tile_count, s->chunk_count, s->chunk_total, s->done_counter, s->index_base, s->visible, s->visible_count));
+	                           s->tile_count, s->chunk_count, (const uint32_t*)totals, totals_next, s->index_base, s->visible, s->visible_count));
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
 	return ZN_OK;
 }
