@@ -145,7 +145,9 @@ typedef struct zn_scene_buffers {
 	void* visible;          /* uint32[E], first *visible_count entries valid, ascending */
 	void* visible_count;    /* uint32[1] */
 	void* visibility_record;          /* uint32[visibility_record_words]: the frame's visible set at 1 bit per
-	                                     entity — per-chunk counts, then 8 mask words per 256-entity tile */
+	                                     entity — a header of list offsets per 8192-entity chunk and the total
+	                                     count, then 8 mask words per 256-entity tile.  Opaque: produced by
+	                                     zn_scene_update, consumed by zn_scene_expand_visible. */
 	uint32_t visibility_record_words;
 	uint32_t entity_count;
 } zn_scene_buffers;

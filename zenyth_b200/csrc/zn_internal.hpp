@@ -78,7 +78,8 @@ struct zn_scene {
 	uint32_t* visible_count = nullptr; // [1] device
 	uint32_t* visible_own = nullptr;
 	uint32_t* visible_count_own = nullptr;
-	// visibility record of a frame: [chunks] per-chunk visible counts, then [tiles][8] mask words
+	// visibility record of a frame: header (chunk bases, total, group offsets; see
+	// record_header_words in zn_scene.cu), then [tiles][8] mask words
 	uint32_t* record = nullptr;            // where the kernels write (own buffer or a bound one)
 	uint32_t* record_own = nullptr;
 	uint32_t record_words = 0;

@@ -4,9 +4,11 @@
 //       TRS -> local -> world (= parent.world * local) -> MVP -> AABB-vs-frustum flag, plus the
 //       tile's 256-bit visibility mask.
 //   emit_visible_kernel             one launch per frame (K3): ordered visible list from the masks,
-//       single pass — per-chunk popcount, decoupled look-back across chunks, ascending scatter.
+//       single pass — a chunk's base is the sum of the chunk totals before it, then an ascending
+//       warp-cooperative scatter; also fills the header of the frame's visibility record.
+//   expand_visible_kernel           multi-GPU: all-gathered visibility records -> every rank's list.
 //
-// scene_level_kernel is PERSISTENT (4 CTAs of 256 threads per SM, each walking tiles b, b+G, ...)
+// scene_level_kernel is PERSISTENT (4 CTAs of 256 threads per SM, tiles claimed by atomic ticket)
 // and software-pipelined with the TMA unit:
 //   - a tile's inputs are ONE cp.async.bulk (SASS UBLKCP) of its 16 KiB tile-major block, plus one
 //     bulk copy of its contiguous parent-matrix range; thread 0 issues the copies for tile n+1 as
@@ -276,8 +278,8 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 }
 
 // K3: the frame's own ordered visible list.  The level kernels accumulated every chunk's visible
-// count (chunk_total, one atomicAdd per tile).  Each CTA also stores its chunk's count into the
-// frame's visibility record (record = [chunks totals][tiles x 8 mask words]) — the 1-bit-per-entity
+// count (chunk_total, one atomicAdd per tile).  Each CTA also stores the offsets it derived (chunk
+// base, group offsets) into the header of the frame's visibility record — the 1-bit-per-entity
 // form of the result that a multi-GPU exchange ships instead of the 32-bit-per-visible-entity
 // list.  The accumulators are double-buffered by frame parity: while reading this frame's set,
 // every CTA clears its own entry of the OTHER set (last read by the previous frame's emit), so the
@@ -496,14 +498,11 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 		offs = {0u, E};
 	}
 	ZN_CUDA(cudaSetDevice(ctx->device));
-	static bool attr_set = false;
-	if (!attr_set) {
-		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLevelSmem)));
-		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLevelSmem)));
-		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-		ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-		attr_set = true;
-	}
+	// function attributes are per device: set them for every scene (a process may drive several GPUs)
+	ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLevelSmem)));
+	ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLevelSmem)));
+	ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+	ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 	zn_scene* s = new zn_scene();
 	s->ctx = ctx;
 	s->entity_count = E;

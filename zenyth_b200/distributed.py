@@ -185,17 +185,22 @@ class RecordExchange:
     while frame k+1 is computed, and frame k is expanded right after frame k+1's update.
     """
 
-    def __init__(self, record_words: int, capacity: int, world_size: int, device, dtype, slots: int = 2, group=None):
+    def __init__(self, record_words: int, capacity: int, world_size: int, device, dtype, slots: int = 2, group=None,
+                 records_per_rank: int = 1):
         import torch
         self.world_size, self.record_words, self.capacity, self.slots, self.group = world_size, int(record_words), int(capacity), slots, group
-        self.local = [torch.zeros(self.record_words, dtype=dtype, device=device) for _ in range(slots)]
-        self.gathered = [torch.empty(world_size * self.record_words, dtype=dtype, device=device) for _ in range(slots)]
-        self.lists = torch.empty(world_size * self.capacity, dtype=dtype, device=device)
-        self.counts = torch.zeros(world_size, dtype=dtype, device=device)
+        self.records_per_rank = int(records_per_rank)          # a rank that owns several scenes ships them together
+        self.total_records = world_size * self.records_per_rank
+        rank_words = self.record_words * self.records_per_rank
+        self.local = [torch.zeros(rank_words, dtype=dtype, device=device) for _ in range(slots)]
+        self.gathered = [torch.empty(world_size * rank_words, dtype=dtype, device=device) for _ in range(slots)]
+        self.lists = torch.empty(self.total_records * self.capacity, dtype=dtype, device=device)
+        self.counts = torch.zeros(self.total_records, dtype=dtype, device=device)
         self.work = [None] * slots
 
-    def record_ptr(self, slot: int) -> int:
-        return self.local[slot].data_ptr()
+    def record_ptr(self, slot: int, j: int = 0) -> int:
+        """Device address where this rank's j-th scene writes its record for `slot`."""
+        return self.local[slot].data_ptr() + 4 * self.record_words * j
 
     def launch(self, slot: int) -> None:
         import torch.distributed as dist
@@ -212,10 +217,10 @@ class RecordExchange:
 
     def expand(self, scene, slot: int, index_bases=None) -> None:
         """Expand the gathered records of `slot` into self.lists / self.counts on the scene's stream."""
-        scene.ExpandVisible(self.gathered[slot].data_ptr(), self.world_size, self.record_words, self.lists.data_ptr(), self.capacity,
+        scene.ExpandVisible(self.gathered[slot].data_ptr(), self.total_records, self.record_words, self.lists.data_ptr(), self.capacity,
                             self.counts.data_ptr(), index_bases=index_bases)
 
     def result(self):
-        """(counts, lists[world, capacity]) of the most recently expanded frame (synchronises)."""
+        """(counts, lists[records, capacity]) of the most recently expanded frame (synchronises)."""
         counts = [int(c) for c in self.counts.tolist()]
-        return counts, self.lists.view(self.world_size, self.capacity)
+        return counts, self.lists.view(self.total_records, self.capacity)
