@@ -166,6 +166,16 @@ typedef struct zn_frame_host_io {
 	uint32_t visible_count;     /* out */
 } zn_frame_host_io;
 int zn_scene_frame_host(zn_scene* scene, zn_frame_host_io* io);
+/* The same frame, pipelined: up to two frames in flight.  submit() enqueues the upload of the
+ * packed position/rotation/scale arrays (all three required, page-locked memory for overlap), the
+ * update and the download of the visible count, and returns; wait() completes the OLDEST submitted
+ * frame: fills io->visible_count and, when io->visible is not NULL, io->visible[0..count).  The
+ * upload of frame k+1 overlaps the update and the download of frame k (PCIe is full duplex), so a
+ * steady-state frame costs max(upload, update, download) instead of their sum.  The host arrays
+ * passed to submit() must stay untouched until the matching wait() returns; world/mvp of
+ * zn_frame_host_io are ignored here (they stay on the device: zn_scene_device_buffers). */
+int zn_scene_frame_host_submit(zn_scene* scene, const zn_frame_host_io* io);
+int zn_scene_frame_host_wait(zn_scene* scene, zn_frame_host_io* io);
 
 /* Bytes one zn_scene_update moves by construction: 188 B per root entity,
  * 192 B per child, + 4 B per visible index. */

@@ -198,3 +198,46 @@ def test_visibility_record_expands_to_the_same_list(oracle, gpu_ctx):
     sc.Update()
     assert np.array_equal(sc.Visible(), vis)
     sc.Close()
+
+
+def test_pipelined_host_frames_match_the_oracle(oracle, gpu_ctx):
+    """zn_scene_frame_host_submit/_wait: two frames in flight, each with its own inputs."""
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 4)
+    E = sum(sizes)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    view, proj = camera(oracle)
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    frames = []
+    for f in range(5):   # every frame moves and spins the roots differently
+        a = {k: v.copy() for k, v in arrays.items()}
+        a["rotation"][:7, 1] += np.float32(0.3 * f)
+        a["position"][:7, 0] += np.float32(100.0 * f)
+        frames.append(a)
+    expect = [oracle.scene_update(a, view, proj)["visible"] for a in frames]
+    pinned = [[gpu_ctx.HostAlloc((E, 3), np.float32) for _ in range(3)] for _ in range(2)]
+    out = [gpu_ctx.HostAlloc((E,), np.uint32) for _ in range(2)]
+    got = []
+
+    def submit(f):
+        p, r, s = pinned[f % 2]
+        p[:] = frames[f]["position"]; r[:] = frames[f]["rotation"]; s[:] = frames[f]["scale"]
+        sc.SubmitFrameHost(p, r, s)
+
+    submit(0)
+    submit(1)
+    with pytest.raises(zn.ZenythError):
+        submit(2)                                   # a third frame in flight is refused
+    for f in range(5):
+        n = sc.WaitFrameHost(out[f % 2])
+        got.append(out[f % 2][:n].copy())
+        if f + 2 < 5:
+            submit(f + 2)
+    with pytest.raises(zn.ZenythError):
+        sc.WaitFrameHost(out[0])                    # nothing left in flight
+    for f in range(5):
+        assert np.array_equal(got[f], expect[f]), f
+    assert same_values(sc.World(), oracle.scene_update(frames[4], view, proj)["world"])
+    sc.Close()

@@ -83,6 +83,8 @@ PROTOTYPES = {
     "zn_scene_read_inputs": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]),
     "zn_scene_device_buffers": (C.c_int, [vp, C.POINTER(SceneBuffers)]),
     "zn_scene_frame_host": (C.c_int, [vp, C.POINTER(FrameHostIO)]),
+    "zn_scene_frame_host_submit": (C.c_int, [vp, C.POINTER(FrameHostIO)]),
+    "zn_scene_frame_host_wait": (C.c_int, [vp, C.POINTER(FrameHostIO)]),
     "zn_scene_algorithmic_bytes": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint64)]),
     "zn_scene_launches_per_update": (C.c_int, [vp, c_u32_p]),
     "zn_scene_set_profiling": (C.c_int, [vp, C.c_int]),

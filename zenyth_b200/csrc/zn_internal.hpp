@@ -91,6 +91,7 @@ struct zn_scene {
 	uint32_t* host_count = nullptr;      // pinned [1]
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events; // [levels+2]
+	struct zn_pipe* pipe = nullptr;       // pipelined host frames (zn_scene_frame_host_submit/wait), lazily created
 };
 
 struct zn_mesh_tile {

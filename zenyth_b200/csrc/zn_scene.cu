@@ -562,6 +562,8 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	return ZN_OK;
 }
 
+static void pipe_destroy(zn_scene* s);
+
 int zn_scene_destroy(zn_scene* s) {
 	if (!s) return ZN_OK;
 	cudaSetDevice(s->ctx->device);
@@ -570,6 +572,7 @@ int zn_scene_destroy(zn_scene* s) {
 	cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->level_ticket); cudaFree(s->record_own); cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
 	for (auto e : s->prof_events) cudaEventDestroy(e);
+	pipe_destroy(s);
 	delete s;
 	return ZN_OK;
 }
@@ -865,6 +868,121 @@ int zn_scene_frame_host(zn_scene* s, zn_frame_host_io* io) {
 		ZN_CUDA(cudaMemcpyAsync(io->visible, s->visible, size_t(io->visible_count) * 4, cudaMemcpyDeviceToHost, ctx->stream));
 		ZN_CUDA(cudaStreamSynchronize(ctx->stream));
 	}
+	return ZN_OK;
+}
+
+// ---- pipelined end-to-end frames --------------------------------------------------------------
+// Two frames in flight over three streams: H2D of frame k+1 (upload stream) overlaps the update of
+// frame k (context stream) and the D2H of frame k's visible list (download stream).  PCIe is full
+// duplex, so in steady state a frame costs max(H2D, update, D2H) instead of their sum.  Each slot
+// owns its staging (3 x E x 12 bytes) and its visible list / count buffers.
+struct zn_pipe {
+	cudaStream_t up = nullptr;
+	cudaStream_t down[2] = {nullptr, nullptr};   // one per slot: frame k's list copy must not queue behind frame k+1's count copy
+	uint8_t* staging[2] = {nullptr, nullptr};
+	uint32_t* vis[2] = {nullptr, nullptr};
+	uint32_t* cnt[2] = {nullptr, nullptr};
+	uint32_t* host_cnt = nullptr;                 // pinned [2]
+	cudaEvent_t h2d[2], repacked[2], done[2], counted[2];
+	uint64_t submitted = 0, collected = 0;
+};
+
+static int pipe_create(zn_scene* s) {
+	if (s->pipe) return ZN_OK;
+	zn_pipe* p = new zn_pipe();
+	const size_t E = s->entity_count;
+	ZN_CUDA(cudaStreamCreateWithFlags(&p->up, cudaStreamNonBlocking));
+	ZN_CUDA(cudaHostAlloc(&p->host_cnt, 8, cudaHostAllocDefault));
+	for (int k = 0; k < 2; ++k) {
+		ZN_CUDA(cudaStreamCreateWithFlags(&p->down[k], cudaStreamNonBlocking));
+		ZN_CUDA(cudaMalloc(&p->staging[k], E * 36));
+		ZN_CUDA(cudaMalloc(&p->vis[k], E * 4));
+		ZN_CUDA(cudaMalloc(&p->cnt[k], 4));
+		ZN_CUDA(cudaEventCreateWithFlags(&p->h2d[k], cudaEventDisableTiming));
+		ZN_CUDA(cudaEventCreateWithFlags(&p->repacked[k], cudaEventDisableTiming));
+		ZN_CUDA(cudaEventCreateWithFlags(&p->done[k], cudaEventDisableTiming));
+		ZN_CUDA(cudaEventCreateWithFlags(&p->counted[k], cudaEventDisableTiming));
+	}
+	s->pipe = p;
+	return ZN_OK;
+}
+
+static void pipe_destroy(zn_scene* s) {
+	zn_pipe* p = s->pipe;
+	if (!p) return;
+	if (p->up) cudaStreamSynchronize(p->up);
+	for (int k = 0; k < 2; ++k) if (p->down[k]) cudaStreamSynchronize(p->down[k]);
+	for (int k = 0; k < 2; ++k) {
+		cudaFree(p->staging[k]); cudaFree(p->vis[k]); cudaFree(p->cnt[k]);
+		cudaEventDestroy(p->h2d[k]); cudaEventDestroy(p->repacked[k]); cudaEventDestroy(p->done[k]); cudaEventDestroy(p->counted[k]);
+	}
+	if (p->host_cnt) cudaFreeHost(p->host_cnt);
+	if (p->up) cudaStreamDestroy(p->up);
+	for (int k = 0; k < 2; ++k) if (p->down[k]) cudaStreamDestroy(p->down[k]);
+	delete p;
+	s->pipe = nullptr;
+}
+
+int zn_scene_frame_host_submit(zn_scene* s, const zn_frame_host_io* io) {
+	ZN_REQUIRE(s && io, "zn_scene_frame_host_submit: NULL argument");
+	ZN_REQUIRE(io->position && io->rotation && io->scale, "zn_scene_frame_host_submit: position, rotation and scale are required");
+	if (!s->has_camera) return fail(ZN_ERR_STATE, "zn_scene_frame_host_submit: no camera set");
+	zn_ctx* ctx = s->ctx;
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	int rc = pipe_create(s);
+	if (rc != ZN_OK) return rc;
+	zn_pipe* p = s->pipe;
+	if (p->submitted - p->collected >= 2) return fail(ZN_ERR_STATE, "zn_scene_frame_host_submit: two frames are already in flight; call zn_scene_frame_host_wait");
+	const int k = int(p->submitted & 1);
+	const size_t E = s->entity_count, bytes = E * 12;
+	// upload stream: wait until the slot's previous contents have been repacked, then three big copies
+	if (p->submitted >= 2) ZN_CUDA(cudaStreamWaitEvent(p->up, p->repacked[k], 0));
+	const float* src[3] = {io->position, io->rotation, io->scale};
+	for (int a = 0; a < 3; ++a)
+		ZN_CUDA(cudaMemcpyAsync(p->staging[k] + a * bytes, src[a], bytes, cudaMemcpyHostToDevice, p->up));
+	ZN_CUDA(cudaEventRecord(p->h2d[k], p->up));
+	// context stream: repack into the tile-major blocks, update into this slot's list buffers
+	ZN_CUDA(cudaStreamWaitEvent(ctx->stream, p->h2d[k], 0));
+	for (int a = 0; a < 3; ++a) {
+		rc = for_each_level_range(s, 0, s->entity_count, [&](const zn_level& lv, uint32_t lo, uint32_t hi) {
+			const uint32_t* from = reinterpret_cast<const uint32_t*>(p->staging[k] + a * bytes) + size_t(lo) * 3;
+			repack3_kernel<<<(hi - lo + 255) / 256, 256, 0, ctx->stream>>>(from, 3, hi - lo, s->blocks, lv.tile_base, lo - lv.begin, 3 * a);
+			return ZN_OK;
+		});
+		if (rc != ZN_OK) return rc;
+	}
+	ZN_CUDA(cudaGetLastError());
+	ZN_CUDA(cudaEventRecord(p->repacked[k], ctx->stream));
+	uint32_t* keep_vis = s->visible;
+	uint32_t* keep_cnt = s->visible_count;
+	s->visible = p->vis[k];
+	s->visible_count = p->cnt[k];
+	rc = zn_scene_update(s);
+	s->visible = keep_vis;
+	s->visible_count = keep_cnt;
+	if (rc != ZN_OK) return rc;
+	ZN_CUDA(cudaEventRecord(p->done[k], ctx->stream));
+	// download stream: the count first (the list's size is not known on the host yet)
+	ZN_CUDA(cudaStreamWaitEvent(p->down[k], p->done[k], 0));
+	ZN_CUDA(cudaMemcpyAsync(p->host_cnt + k, p->cnt[k], 4, cudaMemcpyDeviceToHost, p->down[k]));
+	ZN_CUDA(cudaEventRecord(p->counted[k], p->down[k]));
+	p->submitted++;
+	return ZN_OK;
+}
+
+int zn_scene_frame_host_wait(zn_scene* s, zn_frame_host_io* io) {
+	ZN_REQUIRE(s && io, "zn_scene_frame_host_wait: NULL argument");
+	zn_pipe* p = s->pipe;
+	if (!p || p->collected == p->submitted) return fail(ZN_ERR_STATE, "zn_scene_frame_host_wait: no frame in flight");
+	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	const int k = int(p->collected & 1);
+	ZN_CUDA(cudaEventSynchronize(p->counted[k]));
+	io->visible_count = p->host_cnt[k];
+	if (io->visible && io->visible_count) {
+		ZN_CUDA(cudaMemcpyAsync(io->visible, p->vis[k], size_t(io->visible_count) * 4, cudaMemcpyDeviceToHost, p->down[k]));
+		ZN_CUDA(cudaStreamSynchronize(p->down[k]));
+	}
+	p->collected++;
 	return ZN_OK;
 }
 

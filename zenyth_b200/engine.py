@@ -257,6 +257,17 @@ class Scene:
         check(self._lib.zn_scene_frame_host(self._h, C.byref(io)))
         return int(io.visible_count)
 
+    def SubmitFrameHost(self, position, rotation, scale) -> None:
+        """Pipelined end-to-end frame (zn_scene_frame_host_submit): at most two in flight."""
+        io = _capi.FrameHostIO(_p(position), _p(rotation), _p(scale), None, None, None, 0)
+        check(self._lib.zn_scene_frame_host_submit(self._h, C.byref(io)))
+
+    def WaitFrameHost(self, visible=None) -> int:
+        """Complete the oldest submitted frame; returns its visible count (and fills `visible`)."""
+        io = _capi.FrameHostIO(None, None, None, None, None, _p(visible), 0)
+        check(self._lib.zn_scene_frame_host_wait(self._h, C.byref(io)))
+        return int(io.visible_count)
+
     # -- results ------------------------------------------------------------------------------
     def VisibleCount(self) -> int:
         n = C.c_uint32()
