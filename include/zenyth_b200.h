@@ -153,6 +153,15 @@ typedef struct zn_scene_buffers {
 } zn_scene_buffers;
 int zn_scene_device_buffers(zn_scene* scene, zn_scene_buffers* out);
 
+/* What the draw submission after IRenderer::EndFrame (Core/include/IRenderer.hpp:10) consumes,
+ * built on the device from the last update: instance_mvp_dev[k] = mvp[visible[k]] for k in
+ * [0, count) (float[instance_capacity][16], instance_capacity >= entity_count) and one argument
+ * record at draw_args_dev in the D3D12_DRAW_INDEXED_ARGUMENTS layout — five 32-bit words
+ * {index_count_per_instance, count, 0, 0, 0}.  No host round trip: the count is read on the
+ * device.  Asynchronous on the context stream. */
+int zn_scene_build_draw(zn_scene* scene, uint32_t index_count_per_instance, void* instance_mvp_dev, uint32_t instance_capacity,
+                        void* draw_args_dev);
+
 /* End-to-end frame with HOST buffers: uploads the packed [E][3] inputs (NULL = keep what is
  * resident), runs the frame, downloads what is asked for (NULL = leave on the device), and
  * returns after the data has landed.  This is the call a CPU engine would swap in. */

@@ -200,6 +200,11 @@ public:
 		detail::Check(zn_scene_device_buffers(m_scene, &b), "Scene::DeviceBuffers");
 		return b;
 	}
+	// Visible list -> packed per-instance MVP buffer + one D3D12_DRAW_INDEXED_ARGUMENTS record, both
+	// in caller-owned device memory, built on the device (no host round trip).
+	void BuildDraw(uint32_t indexCountPerInstance, void* instanceMvpDevice, uint32_t instanceCapacity, void* drawArgsDevice) {
+		detail::Check(zn_scene_build_draw(m_scene, indexCountPerInstance, instanceMvpDevice, instanceCapacity, drawArgsDevice), "Scene::BuildDraw");
+	}
 	[[nodiscard]] zn_scene* Handle() const noexcept { return m_scene; }
 
 private:

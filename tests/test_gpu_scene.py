@@ -241,3 +241,31 @@ def test_pipelined_host_frames_match_the_oracle(oracle, gpu_ctx):
         assert np.array_equal(got[f], expect[f]), f
     assert same_values(sc.World(), oracle.scene_update(frames[4], view, proj)["world"])
     sc.Close()
+
+
+def test_build_draw_packs_visible_mvps_and_indirect_args(oracle, gpu_ctx):
+    """N3: visible list -> per-instance MVP buffer + D3D12_DRAW_INDEXED_ARGUMENTS, on the device."""
+    import torch
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 5)
+    E = sum(sizes)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    for eye, base in (((0, 0, 1500), 0), ((0, 0, 0), 4096)):
+        view, proj = camera(oracle, eye=eye)
+        ref = oracle.scene_update(arrays, view, proj)
+        sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+        sc.Load(arrays)
+        sc.SetCamera(zn.Camera(view=view, proj=proj))
+        sc.SetIndexBase(base)
+        sc.Update()
+        inst = torch.full((E, 16), float("nan"), dtype=torch.float32, device="cuda")
+        args = torch.zeros(5, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        sc.BuildDraw(36, inst.data_ptr(), E, args.data_ptr())
+        gpu_ctx.Sync()
+        n = ref["visible"].size
+        assert args.tolist() == [36, n, 0, 0, 0]
+        got = inst.cpu().numpy()
+        assert same_values(got[:n], ref["mvp"][ref["visible"]])          # packed in list order
+        assert np.all(np.isnan(got[n:]))                                 # nothing written past the count
+        sc.Close()

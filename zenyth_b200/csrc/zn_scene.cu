@@ -353,6 +353,31 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 	}
 }
 
+// Visible list -> what a draw submission consumes: the MVP matrices of the
+// visible entities packed in list order, and one indexed-indirect argument record in the
+// D3D12_DRAW_INDEXED_ARGUMENTS layout {IndexCountPerInstance, InstanceCount, StartIndexLocation,
+// BaseVertexLocation, StartInstanceLocation}.  Four threads move one 64-byte matrix, so both the
+// gather (ascending entity order) and the packed store are full 16-byte accesses; the count is
+// read on the device, no host round trip.
+__global__ void __launch_bounds__(256)
+build_draw_kernel(const float4* __restrict__ mvp, const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count,
+                  uint32_t index_base, uint32_t index_count_per_instance, float4* __restrict__ instance_mvp,
+                  uint32_t* __restrict__ draw_args) {
+	const uint32_t count = *visible_count;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		draw_args[0] = index_count_per_instance;
+		draw_args[1] = count;
+		draw_args[2] = 0u;
+		draw_args[3] = 0u;
+		draw_args[4] = 0u;
+	}
+	const uint64_t chunks = uint64_t(count) * 4;
+	for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < chunks; i += uint64_t(gridDim.x) * blockDim.x) {
+		const uint32_t entity = visible[i >> 2] - index_base;
+		instance_mvp[i] = __ldg(mvp + size_t(entity) * 4 + (i & 3));
+	}
+}
+
 // {first parent, parent count} of every tile: one warp per tile over the parent row of its block.
 __global__ void __launch_bounds__(256)
 tile_prange_kernel(const uint32_t* __restrict__ blocks, uint32_t tiles, uint2* __restrict__ out) {
@@ -838,6 +863,19 @@ int zn_scene_read_inputs(zn_scene* s, uint32_t first, uint32_t count, float* pos
 	for (int k = 0; k < 5; ++k)
 		if ((rc = download_rows(s, 3 * k, 3, first, count, outs[k])) != ZN_OK) return rc;
 	return download_rows(s, 15, 1, first, count, parent);
+}
+
+int zn_scene_build_draw(zn_scene* s, uint32_t index_count_per_instance, void* instance_mvp_dev, uint32_t instance_capacity,
+                        void* draw_args_dev) {
+	ZN_REQUIRE(s && instance_mvp_dev && draw_args_dev, "zn_scene_build_draw: NULL argument");
+	ZN_REQUIRE(instance_capacity >= s->entity_count, "zn_scene_build_draw: instance capacity %u < entity_count %u", instance_capacity, s->entity_count);
+	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	const uint32_t grid = uint32_t(std::min<uint64_t>((uint64_t(s->entity_count) * 4 + 255) / 256, uint64_t(s->ctx->sm_count) * 16));
+	build_draw_kernel<<<grid, 256, 0, s->ctx->stream>>>(reinterpret_cast<const float4*>(s->mvp), s->visible, s->visible_count, s->index_base,
+	                                                   index_count_per_instance, static_cast<float4*>(instance_mvp_dev),
+	                                                   static_cast<uint32_t*>(draw_args_dev));
+	ZN_CUDA(cudaGetLastError());
+	return ZN_OK;
 }
 
 int zn_scene_device_buffers(zn_scene* s, zn_scene_buffers* out) {

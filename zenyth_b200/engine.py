@@ -257,6 +257,11 @@ class Scene:
         check(self._lib.zn_scene_frame_host(self._h, C.byref(io)))
         return int(io.visible_count)
 
+    def BuildDraw(self, index_count_per_instance: int, instance_mvp_ptr: int, instance_capacity: int, draw_args_ptr: int) -> None:
+        """Visible list -> packed per-instance MVP buffer + indexed-indirect draw arguments (device pointers)."""
+        check(self._lib.zn_scene_build_draw(self._h, index_count_per_instance, C.c_void_p(instance_mvp_ptr), instance_capacity,
+                                            C.c_void_p(draw_args_ptr)))
+
     def SubmitFrameHost(self, position, rotation, scale) -> None:
         """Pipelined end-to-end frame (zn_scene_frame_host_submit): at most two in flight."""
         io = _capi.FrameHostIO(_p(position), _p(rotation), _p(scale), None, None, None, 0)
