@@ -27,7 +27,7 @@ def build(ref: bool = True) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
     subprocess.run(["make", "-s", "-C", HERE], check=True)
     if ref and os.path.isdir("/root/reference/Core/src/math"):
-        subprocess.run(["make", "-s", "-C", HERE, "ref", "mat4"], check=True)
+        subprocess.run(["make", "-s", "-C", HERE, "ref", "mat4", "loop"], check=True)
 
 
 def _ptr(a, dtype):

@@ -93,3 +93,23 @@ def test_cpp_headless_sandbox_runs_the_reference_loop_shape(gpu_ctx):
     assert r.returncode == 0, r.stdout + r.stderr
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["entities"] == 4681 and 0 < out["visible"] <= 4681 and out["ms_per_frame"] > 0
+
+
+def test_reference_application_loop_drives_the_gpu_scene(gpu_ctx):
+    """SURVEY §8(f) N1: the reference's own Application::Run (Core/src/Application.cpp:26-57) and Timer,
+    compiled in place with a windowless Window, run the config-1 stand-in scene on the GPU through
+    the IRenderer seam.  Skipped where oracle/_ref/sandbox_reference_loop was not built."""
+    import json
+    import os
+
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "sandbox_reference_loop")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/sandbox_reference_loop not built (needs /root/reference at build time)")
+    env = dict(os.environ, ZENYTH_HEADLESS_FRAMES="150")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["entities"] == 4681 and out["frames"] == 150 and out["resizes"] == 1
+    assert 0 < out["visible"] <= 4681
+    assert abs(out["aspect"] - 2.0) < 1e-3                # Application::OnEvent forwarded the 1600x800 resize to IRenderer::Resize
