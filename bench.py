@@ -104,6 +104,54 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class NvmlSampler:
+    """SM clock / throttle reasons polled through NVML every ~2 ms from a thread DURING the timed
+    region (the timed region is ~10 ms: nvidia-smi's 100 ms loop sees it once or twice)."""
+
+    def __init__(self, gpu_uuid: str):
+        import threading
+
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByUUID(gpu_uuid.encode() if isinstance(gpu_uuid, str) else gpu_uuid)
+        self.sm, self.power, self.reasons = [], [], 0
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self._t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        active = sorted(k for k, bit in names.items() if self.reasons & int(bit))
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "power_w_max": float(max(self.power)) if self.power else None,
+                "samples": len(self.sm), "reasons": active, "source": "NVML polled every ~2 ms during the timed region"}
+
+
+def make_sampler(gpu_uuid: str):
+    try:
+        return NvmlSampler(gpu_uuid)
+    except Exception:
+        return ClockSampler(gpu_uuid)
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle, all host threads, preallocated buffers (first-touch done in warm-up)
 class CpuScene:
@@ -297,7 +345,7 @@ def run_ours(args) -> None:
     gpu_id = str(torch.cuda.get_device_properties(dev).uuid)
     if not gpu_id.startswith("GPU-"):
         gpu_id = "GPU-" + gpu_id
-    sampler = ClockSampler(gpu_id)
+    sampler = make_sampler(gpu_id)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record(stream)
@@ -610,7 +658,7 @@ def run_scenes8(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["mesh64m", "scenes8x32m"], default="h8geo16m")
