@@ -49,6 +49,24 @@ WORKLOADS = {
 CAMERA_EYE = (0.0, 0.0, 1500.0)
 
 
+_JSON_OUT = None
+
+
+def capture_stdout() -> None:
+    """The driver wants ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    line on fd 1), so fd 1 is pointed at stderr for the run and the JSON goes to the real stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit_line(text: str, flush: bool = True) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def level_sizes(roots, levels, fanout):
     return [roots * fanout ** l for l in range(levels)]
 
@@ -236,7 +254,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -262,6 +280,8 @@ def run_ours(args) -> None:
     dev = torch.device("cuda", local_rank)
     distributed = world_size > 1
     if distributed:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
 
     roots, levels, fanout, desc = WORKLOADS[args.workload]
@@ -475,7 +495,7 @@ def run_ours(args) -> None:
             "e2e": e2e,
             "gpu_launches": args.steps * launches_per_update,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(json.dumps(line), flush=True)
     scene.Close()
     ctx.Close()
     if distributed:
@@ -533,7 +553,7 @@ def run_mesh(args) -> None:
             reps += 1
         cpu = {"value": n_i * verts * reps / (time.perf_counter() - t0) / 1e6, "unit": "M vertices/s", "cores": th, "kind": "port",
                "sample": f"{reps} passes over {n_i} instances x {verts} vertices (1/8 of the batch), {th} host threads"}
-    print(json.dumps({
+    emit_line(json.dumps({
         "metric": "vertices_per_second_mesh_transform", "value": V / (ms * 1e-3) / 1e6, "unit": "M vertices/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -564,6 +584,8 @@ def run_scenes8(args) -> None:
     dev = torch.device("cuda", local_rank)
     distributed = world_size > 1
     if distributed:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     total_scenes = 8
     assert total_scenes % world_size == 0
@@ -636,7 +658,7 @@ def run_scenes8(args) -> None:
     if rank == 0:
         peak, peak_src = measured_peaks()
         alg = total_scenes * (14 * 188 + (E - 14) * 192) + 4 * sum(counts)
-        print(json.dumps({
+        emit_line(json.dumps({
             "metric": METRIC, "value": total_scenes * E * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world_size,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -667,6 +689,7 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     args = ap.parse_args()
+    capture_stdout()
     if args.workload == "mesh64m":
         run_mesh(args)
     elif args.workload == "scenes8x32m":

@@ -192,6 +192,46 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 //   [header, header + 8*tiles)   the 256-bit tile masks
 __host__ __device__ inline uint32_t record_header_words(uint32_t chunks) { return (chunks * 9u + 1u + 3u) & ~3u; }
 
+// The scatter of one warp's 32 mask words (4 tiles), staged in shared memory as words w4[8] and
+// list offsets o4[8] (four per LDS.128, broadcast) with the tiles' first indices in first[4].
+// Lane l owns bit l of every word, so the stores of a word are one coalesced ascending run.  A
+// word is warp-uniform, so none of the branches diverge.  Visibility is spatially coherent: most
+// groups of four words are all-ones — 128 consecutive indices, written as one 16-byte store per
+// lane when the destination is 16-byte aligned — or all-zero.
+__device__ __forceinline__ void scatter_warp_words(const uint4* __restrict__ w4, const uint4* __restrict__ o4,
+                                                   const uint32_t* __restrict__ first, int lane, uint32_t lt,
+                                                   uint32_t* __restrict__ visible) {
+#pragma unroll
+	for (int g = 0; g < 8; ++g) {   // words 4g..4g+3 belong to tile g/2 of this warp
+		const uint4 m = w4[g];
+		if ((m.x | m.y | m.z | m.w) == 0u) continue;
+		const uint4 o = o4[g];
+		const uint32_t f0 = first[g >> 1] + (g & 1) * 128;
+		if ((m.x & m.y & m.z & m.w) == 0xffffffffu) {
+			if ((reinterpret_cast<uintptr_t>(visible + o.x) & 15u) == 0u) {
+				const uint32_t v = f0 + lane * 4;
+				*reinterpret_cast<uint4*>(visible + o.x + lane * 4) = make_uint4(v, v + 1, v + 2, v + 3);
+			} else {
+				const uint32_t v = f0 + lane;
+				visible[o.x + lane] = v;
+				visible[o.x + 32 + lane] = v + 32;
+				visible[o.x + 64 + lane] = v + 64;
+				visible[o.x + 96 + lane] = v + 96;
+			}
+			continue;
+		}
+		const uint32_t f = f0 + lane;
+		auto put = [&](uint32_t mw, uint32_t off, uint32_t value) {
+			if (mw == 0xffffffffu) visible[off + lane] = value;
+			else if (mw != 0u && ((mw >> lane) & 1u)) visible[off + __popc(mw & lt)] = value;
+		};
+		put(m.x, o.x, f);
+		put(m.y, o.y, f + 32);
+		put(m.z, o.z, f + 64);
+		put(m.w, o.w, f + 96);
+	}
+}
+
 __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ totals, const uint32_t* __restrict__ masks,
                                                const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t chunks,
                                                uint32_t chunk, uint32_t index_base, uint32_t* __restrict__ visible,
@@ -258,22 +298,7 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint4* w4 = reinterpret_cast<const uint4*>(s_word + warp * 32);
 	const uint4* o4 = reinterpret_cast<const uint4*>(s_off + warp * 32);
-#pragma unroll
-	for (int g = 0; g < 8; ++g) {   // words 4g..4g+3 belong to tile g/2 of this warp
-		const uint4 m = w4[g];
-		const uint4 o = o4[g];
-		const uint32_t f = s_first[warp * 4 + (g >> 1)] + (g & 1) * 128 + lane;
-		// a word is warp-uniform, so these branches never diverge: visibility is spatially coherent
-		// and most words are all-ones (one full 128-byte store) or zero (nothing to do)
-		auto put = [&](uint32_t mw, uint32_t off, uint32_t value) {
-			if (mw == 0xffffffffu) visible[off + lane] = value;
-			else if (mw != 0u && ((mw >> lane) & 1u)) visible[off + __popc(mw & lt)] = value;
-		};
-		put(m.x, o.x, f);
-		put(m.y, o.y, f + 32);
-		put(m.z, o.z, f + 64);
-		put(m.w, o.w, f + 96);
-	}
+	scatter_warp_words(w4, o4, s_first + warp * 4, lane, lt, visible);
 	return s_total;
 }
 
@@ -337,20 +362,7 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint4* w4 = reinterpret_cast<const uint4*>(s_word + warp * 32);
 	const uint4* o4 = reinterpret_cast<const uint4*>(s_off + warp * 32);
-#pragma unroll
-	for (int g = 0; g < 8; ++g) {
-		const uint4 m = w4[g];
-		const uint4 o = o4[g];
-		const uint32_t f = s_first[warp * 4 + (g >> 1)] + (g & 1) * 128 + lane;
-		auto put = [&](uint32_t mw, uint32_t off, uint32_t value) {
-			if (mw == 0xffffffffu) visible[off + lane] = value;
-			else if (mw != 0u && ((mw >> lane) & 1u)) visible[off + __popc(mw & lt)] = value;
-		};
-		put(m.x, o.x, f);
-		put(m.y, o.y, f + 32);
-		put(m.z, o.z, f + 64);
-		put(m.w, o.w, f + 96);
-	}
+	scatter_warp_words(w4, o4, s_first + warp * 4, lane, lt, visible);
 }
 
 // Visible list -> what a draw submission consumes: the MVP matrices of the
