@@ -269,3 +269,31 @@ def test_build_draw_packs_visible_mvps_and_indirect_args(oracle, gpu_ctx):
         assert same_values(got[:n], ref["mvp"][ref["visible"]])          # packed in list order
         assert np.all(np.isnan(got[n:]))                                 # nothing written past the count
         sc.Close()
+
+
+def test_frame_host_with_pageable_buffers_and_matrix_download(oracle, gpu_ctx):
+    """zn_scene_frame_host: plain numpy (pageable) arrays in, world + MVP + visible list out."""
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 4)
+    E = sum(sizes)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    view, proj = camera(oracle)
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.SetBounds(arrays["aabb_center"], arrays["aabb_half"])
+    sc.SetParents(arrays["parent"])
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    world = np.empty((E, 16), np.float32)
+    mvp = np.empty((E, 16), np.float32)
+    vis = np.empty(E, np.uint32)
+    n = sc.FrameHost(arrays["position"], arrays["rotation"], arrays["scale"], world=world, mvp=mvp, visible=vis)
+    ref = oracle.scene_update(arrays, view, proj)
+    assert n == ref["visible"].size and np.array_equal(vis[:n], ref["visible"])
+    assert same_values(world, ref["world"]) and same_values(mvp, ref["mvp"])
+    # inputs omitted: the resident ones are reused; a single-entity edit goes through SetTransform
+    t = zn.Transform(position=(5.0, 6.0, 7.0), rotation=(0.1, 0.2, 0.3), scale=(1.0, 2.0, 3.0))
+    sc.SetTransform(9, t)
+    arrays["position"][9], arrays["rotation"][9], arrays["scale"][9] = t.position, t.rotation, t.scale
+    n = sc.FrameHost(visible=vis)
+    ref = oracle.scene_update(arrays, view, proj)
+    assert n == ref["visible"].size and np.array_equal(vis[:n], ref["visible"]) and same_values(sc.World(), ref["world"])
+    sc.Close()
