@@ -198,6 +198,13 @@ int zn_scene_launches_per_update(zn_scene* scene, uint32_t* out_launches);
 int zn_scene_set_profiling(zn_scene* scene, int enable);
 int zn_scene_level_times(zn_scene* scene, float* out_ms, uint32_t capacity, float* out_tail_ms);
 
+/* Scene ingest: a minimal binary SoA dump (the reference has no on-disk format).  Little-endian:
+ * "ZNSCENE1", uint32 entity_count, uint32 level_count, uint32 level_offsets[level_count+1], then
+ * float32 position[E][3], rotation[E][3], scale[E][3], aabb_center[E][3], aabb_half_extent[E][3],
+ * uint32 parent[E] — 64 bytes per entity.  zn_scene_load creates the scene it reads. */
+int zn_scene_save(zn_scene* scene, const char* path);
+int zn_scene_load(zn_ctx* ctx, const char* path, zn_scene** out_scene);
+
 /* ---- mesh batch: bulk vertex position / normal transform by per-instance model matrices.
  *      pos' = model.transform_point(pos); nrm' = normalize(model.inverse_transpose().transform_normal(nrm))
  *      (Core/include/math/matrix.hpp:43-48).  The Renderer-side preprocessing that would sit

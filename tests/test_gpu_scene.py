@@ -297,3 +297,36 @@ def test_frame_host_with_pageable_buffers_and_matrix_download(oracle, gpu_ctx):
     ref = oracle.scene_update(arrays, view, proj)
     assert n == ref["visible"].size and np.array_equal(vis[:n], ref["visible"]) and same_values(sc.World(), ref["world"])
     sc.Close()
+
+
+def test_scene_file_round_trip(oracle, gpu_ctx, tmp_path):
+    """N4: the ZNSCENE1 dump — a file written with numpy loads into a scene that matches the oracle,
+    and saving that scene reproduces the file byte for byte."""
+    import zenyth_b200 as zn
+    sizes = [5, 300, 1000]
+    arrays = oracle.synth_scene(BASE_SEED + 14, sizes, fanout=4, center_range=0.25)
+    path = tmp_path / "scene.znscene"
+    with open(path, "wb") as f:
+        f.write(b"ZNSCENE1")
+        f.write(np.asarray([sum(sizes), len(sizes)], np.uint32).tobytes())
+        f.write(arrays["level_offsets"].astype(np.uint32).tobytes())
+        for k in ("position", "rotation", "scale", "aabb_center", "aabb_half"):
+            f.write(arrays[k].astype(np.float32).tobytes())
+        f.write(arrays["parent"].astype(np.uint32).tobytes())
+    sc = zn.Scene.LoadFile(gpu_ctx, path)
+    assert sc.entity_count == sum(sizes)
+    view, proj = camera(oracle)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    sc.Update()
+    ref = oracle.scene_update(arrays, view, proj)
+    assert same_values(sc.World(), ref["world"]) and np.array_equal(sc.Visible(), ref["visible"])
+    out = tmp_path / "again.znscene"
+    sc.SaveFile(out)
+    assert out.read_bytes() == path.read_bytes()
+    sc.Close()
+    bad = tmp_path / "bad.znscene"
+    bad.write_bytes(b"NOTASCENE" + bytes(64))
+    with pytest.raises(zn.ZenythError):
+        zn.Scene.LoadFile(gpu_ctx, bad)
+    with pytest.raises(zn.ZenythError):
+        zn.Scene.LoadFile(gpu_ctx, tmp_path / "missing.znscene")

@@ -257,6 +257,26 @@ class Scene:
         check(self._lib.zn_scene_frame_host(self._h, C.byref(io)))
         return int(io.visible_count)
 
+    def SaveFile(self, path: str) -> None:
+        """Write the scene's inputs as a ZNSCENE1 file (zn_scene_save)."""
+        check(self._lib.zn_scene_save(self._h, str(path).encode()))
+
+    @classmethod
+    def LoadFile(cls, ctx: "GpuContext", path: str) -> "Scene":
+        """Create a scene from a ZNSCENE1 file (zn_scene_load)."""
+        lib = _capi.load()
+        h = C.c_void_p()
+        check(lib.zn_scene_load(ctx._h, str(path).encode(), C.byref(h)))
+        with open(path, "rb") as f:
+            f.seek(8)
+            n, levels = np.frombuffer(f.read(8), np.uint32)
+            offsets = np.frombuffer(f.read(4 * (int(levels) + 1)), np.uint32).copy()
+        self = cls.__new__(cls)
+        self._lib, self.ctx, self._h = lib, ctx, h
+        self.entity_count = int(n)
+        self.level_offsets = offsets if levels > 1 else None
+        return self
+
     def BuildDraw(self, index_count_per_instance: int, instance_mvp_ptr: int, instance_capacity: int, draw_args_ptr: int) -> None:
         """Visible list -> packed per-instance MVP buffer + indexed-indirect draw arguments (device pointers)."""
         check(self._lib.zn_scene_build_draw(self._h, index_count_per_instance, C.c_void_p(instance_mvp_ptr), instance_capacity,
