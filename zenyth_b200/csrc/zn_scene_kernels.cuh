@@ -1,0 +1,453 @@
+// zn_scene_kernels.cuh — device code of the scene path (included by zn_scene.cu only).
+//
+//
+//   scene_level_kernel<HAS_PARENT>  one launch per hierarchy level (K1/K2 of SURVEY.md §2):
+//       TRS -> local -> world (= parent.world * local) -> MVP -> AABB-vs-frustum flag, plus the
+//       tile's 256-bit visibility mask.
+//   emit_visible_kernel             one launch per frame (K3): ordered visible list from the masks,
+//       single pass — a chunk's base is the sum of the chunk totals before it, then an ascending
+//       warp-cooperative scatter; also fills the header of the frame's visibility record.
+//   expand_visible_kernel           multi-GPU: all-gathered visibility records -> every rank's list.
+//
+// scene_level_kernel is PERSISTENT (4 CTAs of 256 threads per SM, tiles claimed by atomic ticket)
+// and software-pipelined with the TMA unit:
+//   - a tile's inputs are ONE cp.async.bulk (SASS UBLKCP) of its 16 KiB tile-major block, plus one
+//     bulk copy of its contiguous parent-matrix range; thread 0 issues the copies for tile n+1 as
+//     soon as all threads have pulled tile n into registers, so HBM latency hides behind the
+//     sincos / matrix maths of tile n;
+//   - a thread owns one entity; its two 64-byte matrices go to shared memory in the TMA
+//     64-byte-swizzle pattern (conflict-free 16-byte stores) and the tile leaves as two
+//     cp.async.bulk.tensor stores (SASS UTMASTG) that drain while tile n+1 is computed.
+// No thread issues a global load or store for entity data; HBM sees 16 KiB bursts both ways.
+//
+// Data layout in HBM (DESIGN.md "Layout"): inputs are tile-major blocks — for every 256-entity
+// tile one contiguous 16 KiB record of 16 rows x 256 lanes (tx,ty,tz, pitch,yaw,roll, sx,sy,sz,
+// aabb centre xyz, aabb half xyz as float, parent as u32).  Tiles never straddle a hierarchy
+#pragma once
+// level.  Outputs are AoS float[E][16] (what mat4::data() consumers expect,
+// Core/include/math/matrix.hpp:60-61), clipped at the level end by a per-level tensor map.
+#include "zn_internal.hpp"
+#include "zn_math.cuh"
+#include "zn_ptx.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+
+namespace zn {
+
+struct FrameConst {
+	float vp[16];
+	float planes[24];
+};
+
+constexpr int kWarpsPerTile = kTile / 32;                  // 8
+constexpr uint32_t kInBytes = kBlockWords * 4;             // 16 KiB input block
+constexpr uint32_t kParSlots = 64;                         // parent matrices staged per tile
+constexpr uint32_t kParBytes = kParSlots * 64;             // 4 KiB
+constexpr uint32_t kOutBytes = 2 * kTile * 64;             // world tile + mvp tile
+constexpr uint32_t kLevelSmem = kOutBytes + kInBytes + kParBytes + 1024;
+constexpr uint32_t kGather = 0xFFFFFFFFu;                  // tile_prange.y: parents too scattered to stage
+constexpr int kChunkTiles = 32;                            // tiles per emit CTA (8192 entities)
+
+template <bool HAS_PARENT>
+__global__ void __launch_bounds__(kTile, 4)
+scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_constant__ CUtensorMap tm_mvp,
+                   const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
+                   const uint2* __restrict__ tile_prange, const float* __restrict__ world_rd,
+                   uint32_t begin, uint32_t end, uint32_t tile_base, uint32_t tiles,
+                   uint32_t* __restrict__ tile_mask, uint32_t* __restrict__ chunk_total,
+                   uint32_t* __restrict__ ticket, uint32_t ticket_base) {
+	extern __shared__ uint8_t smem_raw[];
+	__shared__ uint64_t s_full;
+	__shared__ uint2 s_meta;
+	__shared__ uint32_t s_mask[kWarpsPerTile];
+	__shared__ uint32_t s_tile[2];   // level-relative tile of iteration n (slot n&1) and n+1
+
+	// 1024-byte aligned tiles (the swizzle pattern is a function of the shared address bits)
+	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	float4* out_world = reinterpret_cast<float4*>(smem);
+	float4* out_mvp = reinterpret_cast<float4*>(smem + kTile * 64);
+	const uint32_t* in_blk = reinterpret_cast<const uint32_t*>(smem + kOutBytes);
+	const float4* in_par = reinterpret_cast<const float4*>(smem + kOutBytes + kInBytes);
+
+	const int t = threadIdx.x;
+	const int lane = t & 31;
+	const int warp = t >> 5;
+
+	// thread 0 is the TMA issuer: loads of tile `tl` into the (single) input stage.  `first_tile`:
+	// the input block does not depend on the previous level's kernel but the parent matrices do,
+	// so under programmatic dependent launch only the second copy waits for it.
+	auto issue_loads = [&](uint32_t tl, bool first_tile) {
+		const uint32_t gt = tile_base + tl;
+		uint2 pr = make_uint2(0u, 0u);
+		if (HAS_PARENT) pr = __ldg(tile_prange + gt);
+		const bool staged = HAS_PARENT && pr.y != 0u && pr.y != kGather;
+		s_meta = pr;
+		mbar_arrive_expect_tx(&s_full, kInBytes + (staged ? pr.y * 64u : 0u));
+		bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, kInBytes, &s_full);
+		if (HAS_PARENT && first_tile) grid_dep_wait();
+		if (staged) bulk_g2s(const_cast<float4*>(in_par), world_rd + size_t(pr.x) * 16, pr.y * 64u, &s_full);
+	};
+
+	if (t == 0) {
+		mbar_init(&s_full, 1);
+		fence_mbar_init();
+		prefetch_tensormap(&tm_world);
+		prefetch_tensormap(&tm_mvp);
+		grid_dep_launch();          // the next level's kernel may start its own prologue now
+		// Tiles are claimed dynamically (one atomic ticket per tile): a CTA that starts late — e.g.
+		// while a collective's kernel holds part of the SMs — simply takes fewer tiles.  The grid is
+		// never larger than the tile count, so every CTA gets at least one tile.
+		const uint32_t tl0 = atomicAdd(ticket, 1u) - ticket_base;
+		s_tile[0] = tl0;
+		if (tl0 < tiles) issue_loads(tl0, true);
+	}
+	__syncthreads();
+
+	for (uint32_t n = 0;; ++n) {
+		const uint32_t tl = s_tile[n & 1u];
+		if (tl >= tiles) break;
+		// ---- tile n: shared memory -> registers ------------------------------------------------
+		mbar_wait(&s_full, n & 1u);
+		float v[15];
+#pragma unroll
+		for (int k = 0; k < 15; ++k) v[k] = __uint_as_float(in_blk[k * kTile + t]);
+		const uint32_t p = HAS_PARENT ? in_blk[15 * kTile + t] : ZN_NO_PARENT;
+		Affine P;
+		if (HAS_PARENT && p != ZN_NO_PARENT) {
+			const uint2 pr = s_meta;
+			float4 c0, c1, c2, c3;
+			if (pr.y != kGather) {
+				const float4* src = in_par + size_t(p - pr.x) * 4;
+				c0 = src[0]; c1 = src[1]; c2 = src[2]; c3 = src[3];
+			} else {
+				const float4* src = reinterpret_cast<const float4*>(world_rd) + size_t(p) * 4;
+				c0 = __ldg(src); c1 = __ldg(src + 1); c2 = __ldg(src + 2); c3 = __ldg(src + 3);
+			}
+			P.m[0][0] = c0.x; P.m[1][0] = c0.y; P.m[2][0] = c0.z;
+			P.m[0][1] = c1.x; P.m[1][1] = c1.y; P.m[2][1] = c1.z;
+			P.m[0][2] = c2.x; P.m[1][2] = c2.y; P.m[2][2] = c2.z;
+			P.m[0][3] = c3.x; P.m[1][3] = c3.y; P.m[2][3] = c3.z;
+		}
+		if (t == 0) bulk_wait_read_all();   // tile n-1's tensor stores have finished reading the out tile
+		__syncthreads();                    // input stage consumed by everyone; out tile free
+
+		// ---- prefetch tile n+1 while tile n is computed ------------------------------------------
+		if (t == 0) {
+			const uint32_t next = atomicAdd(ticket, 1u) - ticket_base;
+			s_tile[(n + 1u) & 1u] = next;   // read by everyone after the barrier below
+			if (next < tiles) issue_loads(next, false);
+		}
+
+		// ---- tile n: maths in registers ----------------------------------------------------------
+		const Affine local = local_trs(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+		Affine w = local;
+		if (HAS_PARENT && p != ZN_NO_PARENT) w = affine_mul(P, local);
+		const uint32_t first = begin + tl * kTile;
+		const bool vis = (first + t < end) && aabb_visible(w, v[9], v[10], v[11], v[12], v[13], v[14], fc.planes);
+		const uint32_t mask = __ballot_sync(0xffffffffu, vis);
+		if (lane == 0) s_mask[warp] = mask;
+
+		// ---- results -> swizzled shared tile (chunk c of row r lives at chunk c ^ ((r>>1)&3)) ------
+		{
+			const int sw = (t >> 1) & 3;
+			float4* wr = out_world + t * 4;
+			wr[0 ^ sw] = make_float4(w.m[0][0], w.m[1][0], w.m[2][0], 0.0f);
+			wr[1 ^ sw] = make_float4(w.m[0][1], w.m[1][1], w.m[2][1], 0.0f);
+			wr[2 ^ sw] = make_float4(w.m[0][2], w.m[1][2], w.m[2][2], 0.0f);
+			wr[3 ^ sw] = make_float4(w.m[0][3], w.m[1][3], w.m[2][3], 1.0f);
+			float m[16];
+			mvp_mul(fc.vp, w, m);
+			float4* mr = out_mvp + t * 4;
+			mr[0 ^ sw] = make_float4(m[0], m[1], m[2], m[3]);
+			mr[1 ^ sw] = make_float4(m[4], m[5], m[6], m[7]);
+			mr[2 ^ sw] = make_float4(m[8], m[9], m[10], m[11]);
+			mr[3 ^ sw] = make_float4(m[12], m[13], m[14], m[15]);
+		}
+		fence_proxy_async_smem();
+		__syncthreads();
+		if (t == 0) {
+			tensor_store_2d(&tm_world, out_world, 0, int32_t(first));
+			tensor_store_2d(&tm_mvp, out_mvp, 0, int32_t(first));
+			bulk_commit();
+		}
+		if (warp == 0) {
+			const uint32_t gt = tile_base + tl;
+			const uint32_t word = (lane < kWarpsPerTile) ? s_mask[lane] : 0u;
+			if (lane < kWarpsPerTile) tile_mask[size_t(gt) * kWarpsPerTile + lane] = word;
+			const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(word));
+			if (lane == 0) atomicAdd(chunk_total + gt / kChunkTiles, cnt);
+		}
+	}
+	if (t == 0) bulk_wait_read_all();
+}
+
+// One chunk (32 tiles = 8192 entities) of an ordered visible list: `totals` holds every chunk's
+// visible count, `masks` the 256-bit tile masks.  The CTA gets its base offset by summing the
+// totals of the chunks before it — a few KiB of L2 reads, no serial dependency between CTAs —
+// then scatters its set bits in ascending order.  Returns this chunk's own count (in every thread).
+// Visibility record of a frame (what a multi-GPU exchange ships, 1 bit per entity):
+//   [0, chunks)                  exclusive base of every chunk in the visible list
+//   [chunks]                     total visible count
+//   [chunks+1, chunks+1+8*chunks) exclusive offset of every 4-tile group within its chunk
+//   (padding to a multiple of 4 words)
+//   [header, header + 8*tiles)   the 256-bit tile masks
+__host__ __device__ inline uint32_t record_header_words(uint32_t chunks) { return (chunks * 9u + 1u + 3u) & ~3u; }
+
+// The scatter of one warp's 32 mask words (4 tiles), staged in shared memory as words w4[8] and
+// list offsets o4[8] (four per LDS.128, broadcast) with the tiles' first indices in first[4].
+// Lane l owns bit l of every word, so the stores of a word are one coalesced ascending run.  A
+// word is warp-uniform, so none of the branches diverge.  Visibility is spatially coherent: most
+// groups of four words are all-ones — 128 consecutive indices, written as one 16-byte store per
+// lane when the destination is 16-byte aligned — or all-zero.
+__device__ __forceinline__ void scatter_warp_words(const uint4* __restrict__ w4, const uint4* __restrict__ o4,
+                                                   const uint32_t* __restrict__ first, int lane, uint32_t lt,
+                                                   uint32_t* __restrict__ visible) {
+#pragma unroll
+	for (int g = 0; g < 8; ++g) {   // words 4g..4g+3 belong to tile g/2 of this warp
+		const uint4 m = w4[g];
+		if ((m.x | m.y | m.z | m.w) == 0u) continue;
+		const uint4 o = o4[g];
+		const uint32_t f0 = first[g >> 1] + (g & 1) * 128;
+		if ((m.x & m.y & m.z & m.w) == 0xffffffffu) {
+			if ((reinterpret_cast<uintptr_t>(visible + o.x) & 15u) == 0u) {
+				const uint32_t v = f0 + lane * 4;
+				*reinterpret_cast<uint4*>(visible + o.x + lane * 4) = make_uint4(v, v + 1, v + 2, v + 3);
+			} else {
+				const uint32_t v = f0 + lane;
+				visible[o.x + lane] = v;
+				visible[o.x + 32 + lane] = v + 32;
+				visible[o.x + 64 + lane] = v + 64;
+				visible[o.x + 96 + lane] = v + 96;
+			}
+			continue;
+		}
+		const uint32_t f = f0 + lane;
+		auto put = [&](uint32_t mw, uint32_t off, uint32_t value) {
+			if (mw == 0xffffffffu) visible[off + lane] = value;
+			else if (mw != 0u && ((mw >> lane) & 1u)) visible[off + __popc(mw & lt)] = value;
+		};
+		put(m.x, o.x, f);
+		put(m.y, o.y, f + 32);
+		put(m.z, o.z, f + 64);
+		put(m.w, o.w, f + 96);
+	}
+}
+
+__device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ totals, const uint32_t* __restrict__ masks,
+                                               const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t chunks,
+                                               uint32_t chunk, uint32_t index_base, uint32_t* __restrict__ visible,
+                                               uint32_t* __restrict__ visible_count, uint32_t* __restrict__ record_out) {
+	__shared__ uint32_t s_part[8];
+	__shared__ uint32_t s_warp_excl[8];
+	__shared__ uint32_t s_base, s_total;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+	uint32_t acc = 0;
+	for (uint32_t j = t; j < chunk; j += 256) acc += __ldcg(totals + j);
+	acc = __reduce_add_sync(0xffffffffu, acc);
+	if (lane == 0) s_part[warp] = acc;
+
+	// thread t owns mask word t of the chunk: tile chunk*32 + t/8, word t%8
+	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
+	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (t & 7)) : 0u;
+	const uint32_t cnt = __popc(word);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += y;
+	}
+	if (lane == 31) s_warp_excl[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t wt = (lane < 8) ? s_warp_excl[lane] : 0u;
+		uint32_t winc = wt;
+#pragma unroll
+		for (int d = 1; d < 8; d <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, winc, d);
+			if (lane >= d) winc += y;
+		}
+		const uint32_t base = __reduce_add_sync(0xffffffffu, (lane < 8) ? s_part[lane] : 0u);
+		const uint32_t total = __shfl_sync(0xffffffffu, winc, 7);
+		if (lane < 8) {
+			s_warp_excl[lane] = winc - wt;
+			record_out[chunks + 1u + chunk * 8u + lane] = winc - wt;
+		}
+		if (lane == 0) {
+			s_base = base;
+			s_total = total;
+			record_out[chunk] = base;
+			if (chunk == chunks - 1) {
+				*visible_count = base + total;
+				record_out[chunks] = base + total;
+			}
+		}
+	}
+	__syncthreads();
+	const uint32_t my_off = s_base + s_warp_excl[warp] + incl - cnt;   // exclusive offset of this thread's word
+	// warp-cooperative scatter: a warp owns 32 words (4 tiles); every lane tests ITS bit of a word,
+	// so the stores of a word are one coalesced run in ascending order.  The words and offsets are
+	// staged in shared memory and fetched four at a time (one LDS.128 each, broadcast) — the loop
+	// is issue-bound, not bandwidth-bound, so instructions per word are what count.
+	__shared__ __align__(16) uint32_t s_word[256];
+	__shared__ __align__(16) uint32_t s_off[256];
+	__shared__ uint32_t s_first[kChunkTiles];
+	s_word[t] = word;
+	s_off[t] = my_off;
+	if ((t & 7) == 0) s_first[t >> 3] = (tile < tiles) ? tile_first_entity[tile] + index_base : 0u;
+	__syncwarp();
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint4* w4 = reinterpret_cast<const uint4*>(s_word + warp * 32);
+	const uint4* o4 = reinterpret_cast<const uint4*>(s_off + warp * 32);
+	scatter_warp_words(w4, o4, s_first + warp * 4, lane, lt, visible);
+	return s_total;
+}
+
+// K3: the frame's own ordered visible list.  The level kernels accumulated every chunk's visible
+// count (chunk_total, one atomicAdd per tile).  Each CTA also stores the offsets it derived (chunk
+// base, group offsets) into the header of the frame's visibility record — the 1-bit-per-entity
+// form of the result that a multi-GPU exchange ships instead of the 32-bit-per-visible-entity
+// list.  The accumulators are double-buffered by frame parity: while reading this frame's set,
+// every CTA clears its own entry of the OTHER set (last read by the previous frame's emit), so the
+// next frame finds zeros without any cross-CTA handshake.
+__global__ void __launch_bounds__(256)
+emit_visible_kernel(uint32_t* __restrict__ record, const uint32_t* __restrict__ tile_first_entity,
+                    uint32_t tiles, uint32_t chunks, const uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ chunk_total_next,
+                    uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
+	const uint32_t chunk = blockIdx.x;
+	grid_dep_wait();   // masks and totals of every level are complete and visible
+	emit_chunk(chunk_total, record + record_header_words(chunks), tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count, record);
+	if (threadIdx.x == 0) chunk_total_next[chunk] = 0u;
+}
+
+// Expands `gridDim.y` visibility records (this rank's and its peers', as all-gathered) into their
+// ordered index lists: lists[r*list_stride ...], counts[r].  Same arithmetic as emit_visible_kernel,
+// so every rank derives bit-identical lists from the 27x smaller records.
+struct ExpandBases {
+	uint32_t base[64];
+};
+// A record already carries every offset the owner computed (chunk bases, group offsets), so a warp
+// here is autonomous: 32 mask words (4 tiles) + two offsets in, a warp scan, the scatter out — no
+// shared-memory reduction, no block barrier.
+__global__ void __launch_bounds__(256)
+expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
+                      uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, int skip,
+                      uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ counts) {
+	__shared__ __align__(16) uint32_t s_word[256];
+	__shared__ __align__(16) uint32_t s_off[256];
+	__shared__ uint32_t s_first[kChunkTiles];
+	const uint32_t r = blockIdx.y;
+	if (int(r) == skip) return;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const uint32_t* rec = records + size_t(r) * record_stride;
+	const uint32_t* masks = rec + record_header_words(chunks);
+	uint32_t* visible = lists + size_t(r) * list_stride;
+	const uint32_t chunk = blockIdx.x;
+	const uint32_t group = chunk * 8u + warp;                 // 4 tiles = 32 mask words
+	const uint32_t tile = group * 4u + (lane >> 3);
+	if (tile - (lane >> 3) >= tiles) return;                  // whole group past the end (warp-uniform)
+	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
+	const uint32_t base = __ldcg(rec + chunk) + __ldcg(rec + chunks + 1u + group);
+	if (chunk == 0 && t == 0) counts[r] = __ldcg(rec + chunks);
+	const uint32_t cnt = __popc(word);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += y;
+	}
+	s_word[t] = word;
+	s_off[t] = base + incl - cnt;
+	if ((lane & 7) == 0) s_first[t >> 3] = (tile < tiles) ? tile_first_entity[tile] + bases.base[r] : 0u;
+	__syncwarp();
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint4* w4 = reinterpret_cast<const uint4*>(s_word + warp * 32);
+	const uint4* o4 = reinterpret_cast<const uint4*>(s_off + warp * 32);
+	scatter_warp_words(w4, o4, s_first + warp * 4, lane, lt, visible);
+}
+
+// Visible list -> what a draw submission consumes: the MVP matrices of the
+// visible entities packed in list order, and one indexed-indirect argument record in the
+// D3D12_DRAW_INDEXED_ARGUMENTS layout {IndexCountPerInstance, InstanceCount, StartIndexLocation,
+// BaseVertexLocation, StartInstanceLocation}.  Four threads move one 64-byte matrix, so both the
+// gather (ascending entity order) and the packed store are full 16-byte accesses; the count is
+// read on the device, no host round trip.
+__global__ void __launch_bounds__(256)
+build_draw_kernel(const float4* __restrict__ mvp, const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count,
+                  uint32_t index_base, uint32_t index_count_per_instance, float4* __restrict__ instance_mvp,
+                  uint32_t* __restrict__ draw_args) {
+	const uint32_t count = *visible_count;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		draw_args[0] = index_count_per_instance;
+		draw_args[1] = count;
+		draw_args[2] = 0u;
+		draw_args[3] = 0u;
+		draw_args[4] = 0u;
+	}
+	const uint64_t chunks = uint64_t(count) * 4;
+	for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < chunks; i += uint64_t(gridDim.x) * blockDim.x) {
+		const uint32_t entity = visible[i >> 2] - index_base;
+		instance_mvp[i] = __ldg(mvp + size_t(entity) * 4 + (i & 3));
+	}
+}
+
+// {first parent, parent count} of every tile: one warp per tile over the parent row of its block.
+__global__ void __launch_bounds__(256)
+tile_prange_kernel(const uint32_t* __restrict__ blocks, uint32_t tiles, uint2* __restrict__ out) {
+	const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (tile >= tiles) return;
+	const int lane = threadIdx.x & 31;
+	const uint32_t* row = blocks + size_t(tile) * kBlockWords + 15 * kTile;
+	uint32_t lo = ZN_NO_PARENT, hi = 0;
+#pragma unroll
+	for (int k = 0; k < kTile / 32; ++k) {
+		const uint32_t p = row[k * 32 + lane];
+		lo = min(lo, p);
+		hi = max(hi, p == ZN_NO_PARENT ? 0u : p);
+	}
+	lo = __reduce_min_sync(0xffffffffu, lo);
+	hi = __reduce_max_sync(0xffffffffu, hi);
+	if (lane == 0) {
+		uint2 r = make_uint2(0u, 0u);
+		if (lo != ZN_NO_PARENT) r = make_uint2(lo, (hi - lo < kParSlots) ? hi - lo + 1u : kGather);
+		out[tile] = r;
+	}
+}
+
+__global__ void init_parent_rows_kernel(uint32_t* __restrict__ blocks, uint32_t tiles) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < tiles * kTile) blocks[size_t(i / kTile) * kBlockWords + 15 * kTile + (i % kTile)] = ZN_NO_PARENT;
+}
+
+// Strided host records (3 words every `stride_w` words) of level-relative entities
+// [rel_first, rel_first+count) -> rows row0..row0+2 of the tile-major blocks.
+__global__ void repack3_kernel(const uint32_t* __restrict__ src, uint32_t stride_w, uint32_t count,
+                               uint32_t* __restrict__ blocks, uint32_t tile_base, uint32_t rel_first, int row0) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= count) return;
+	const uint32_t rel = rel_first + j;
+	uint32_t* d = blocks + size_t(tile_base + rel / kTile) * kBlockWords + row0 * kTile + (rel % kTile);
+	const uint32_t* s = src + size_t(j) * stride_w;
+	d[0] = s[0]; d[kTile] = s[1]; d[2 * kTile] = s[2];
+}
+__global__ void repack1_kernel(const uint32_t* __restrict__ src, uint32_t count, uint32_t* __restrict__ blocks,
+                               uint32_t tile_base, uint32_t rel_first, int row) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= count) return;
+	const uint32_t rel = rel_first + j;
+	blocks[size_t(tile_base + rel / kTile) * kBlockWords + row * kTile + (rel % kTile)] = src[j];
+}
+// rows row0..row0+nrows-1 of the blocks -> packed [count][nrows] words
+__global__ void unpack_kernel(const uint32_t* __restrict__ blocks, uint32_t tile_base, uint32_t rel_first, uint32_t count,
+                              int row0, int nrows, uint32_t* __restrict__ dst) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= count) return;
+	const uint32_t rel = rel_first + j;
+	const uint32_t* s = blocks + size_t(tile_base + rel / kTile) * kBlockWords + row0 * kTile + (rel % kTile);
+	for (int r = 0; r < nrows; ++r) dst[size_t(j) * nrows + r] = s[r * kTile];
+}
+
+
+} // namespace zn
