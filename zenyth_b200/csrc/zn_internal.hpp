@@ -97,8 +97,8 @@ struct zn_scene {
 struct zn_mesh_tile {
 	uint32_t first_vertex;
 	uint32_t vertex_count;
-	uint32_t instance;
-	uint32_t flags;                // bit0: bulk (TMA) path eligible
+	uint32_t instance_lo;          // instances [instance_lo, instance_hi] own vertices of this tile
+	uint32_t instance_hi;
 };
 
 struct zn_mesh {
@@ -112,5 +112,8 @@ struct zn_mesh {
 	float* pos_out = nullptr;
 	float* nrm_out = nullptr;
 	float* models_own = nullptr;     // [I][16]
+	uint32_t* instance_first_vertex = nullptr;  // device [I+1]
+	float* inst_mats = nullptr;      // [I][24] model rows + normal matrix, only when a tile spans several instances
+	bool multi_instance_tiles = false;
 	const float* models = nullptr;   // models_own or a scene's world array
 };

@@ -3,14 +3,17 @@
 //   pos' = model.transform_point(pos)                                   (matrix.hpp:45-46)
 //   nrm' = normalize(model.inverse_transpose().transform_normal(nrm))   (matrix.hpp:43,47-48)
 //
-// Vertices are packed float[V][3] streams (48 algorithmic bytes per vertex in + out).  A CTA owns
-// a tile of up to 1024 vertices of ONE instance: thread 0 pulls the tile's positions and normals
-// into shared memory with two cp.async.bulk copies (12 KiB each) while thread 32 inverts the
-// instance's model matrix; every thread then transforms 4 vertices in place (12-word stride:
+// Vertices are packed float[V][3] streams (48 algorithmic bytes per vertex in + out).  The stream
+// is cut into tiles of 1024 vertices regardless of instance boundaries, so every tile is 16-byte
+// aligned: thread 0 pulls the tile's positions and normals into shared memory with two
+// cp.async.bulk copies (12 KiB each), every thread transforms 4 vertices in place (12-word stride:
 // conflict-free float4 shared accesses) and the tile leaves as two bulk stores.  No thread issues
-// a global load or store for vertex data on this path, and HBM only sees 12 KiB bursts.
-// Tiles whose range is not 4-vertex aligned take a cooperative LDG/STG path through the same
-// shared buffers.
+// a global load or store for vertex data, and HBM only sees 12 KiB bursts.
+//   - a tile inside ONE instance (the common case for large meshes): thread 32 inverts that
+//     instance's model matrix while the copies are in flight;
+//   - a tile spanning SEVERAL instances (small meshes): the per-instance matrices come from a table
+//     built by mesh_instance_mats_kernel, and a thread finds each vertex's instance by binary
+//     search over the tile's slice of instance_first_vertex staged in shared memory.
 #include "zn_internal.hpp"
 #include "zn_math.cuh"
 #include "zn_ptx.cuh"
@@ -21,34 +24,79 @@
 namespace zn {
 
 constexpr int kMeshThreads = kMeshTileVerts / 4;
+constexpr uint32_t kMeshSmemInstances = 512;   // instance boundaries of a tile staged in shared memory
+constexpr int kInstMatFloats = 24;             // rows 0..2 of the model (12) + 3x3 normal matrix (9) + 3 pad
 
+// Per-instance matrices for tiles that span several instances.
+__global__ void mesh_instance_mats_kernel(const float* __restrict__ models, uint32_t instances, float* __restrict__ out) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= instances) return;
+	float m[16], inv[16];
+	const float4* src = reinterpret_cast<const float4*>(models + size_t(k) * 16);
+#pragma unroll
+	for (int c = 0; c < 4; ++c) {
+		const float4 col = __ldg(src + c);
+		m[c * 4 + 0] = col.x; m[c * 4 + 1] = col.y; m[c * 4 + 2] = col.z; m[c * 4 + 3] = col.w;
+	}
+	mat4_inverse(m, inv);
+	float* o = out + size_t(k) * kInstMatFloats;
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+#pragma unroll
+		for (int c = 0; c < 4; ++c) o[r * 4 + c] = m[c * 4 + r];
+#pragma unroll
+		for (int c = 0; c < 3; ++c) o[12 + r * 3 + c] = inv[r * 4 + c];   // transpose(inverse)(r,c) = inverse(c,r)
+	}
+}
+
+// One vertex: position by the model rows M[12], normal by N[9] then normalised (zero left as is).
+__device__ __forceinline__ void transform_vertex(const float* __restrict__ M, const float* __restrict__ N, float* p, float* n) {
+	const float px = p[0], py = p[1], pz = p[2];
+	const float nx = n[0], ny = n[1], nz = n[2];
+	float q[3], g[3];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		q[r] = add(add(add(mul(M[r * 4 + 0], px), mul(M[r * 4 + 1], py)), mul(M[r * 4 + 2], pz)), M[r * 4 + 3]);
+		g[r] = add(add(mul(N[r * 3 + 0], nx), mul(N[r * 3 + 1], ny)), mul(N[r * 3 + 2], nz));
+	}
+	const float len = __fsqrt_rn(add(add(mul(g[0], g[0]), mul(g[1], g[1])), mul(g[2], g[2])));
+	if (len > 0.0f) { g[0] = __fdiv_rn(g[0], len); g[1] = __fdiv_rn(g[1], len); g[2] = __fdiv_rn(g[2], len); }
+	p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+	n[0] = g[0]; n[1] = g[1]; n[2] = g[2];
+}
+
+// MULTI = false: every tile of the mesh lies inside one instance (the lean kernel the 64Mi-vertex
+// batch runs); MULTI = true also handles tiles that span several instances.
+template <bool MULTI>
 __global__ void __launch_bounds__(kMeshThreads, 4)
 mesh_tile_kernel(const zn_mesh_tile* __restrict__ tiles, const float* __restrict__ models,
+                 const uint32_t* __restrict__ instance_first_vertex, const float* __restrict__ inst_mats,
                  const float* __restrict__ pos_in, const float* __restrict__ nrm_in,
                  float* __restrict__ pos_out, float* __restrict__ nrm_out) {
 	__shared__ __align__(128) float s_pos[kMeshTileVerts * 3];
 	__shared__ __align__(128) float s_nrm[kMeshTileVerts * 3];
 	__shared__ float s_model[12];   // rows 0..2 of the model, row-major [r*4+c]
 	__shared__ float s_nm[9];       // upper 3x3 of (model^-1)^T, row-major
+	__shared__ uint32_t s_first[MULTI ? kMeshSmemInstances + 1 : 1];
 	__shared__ uint64_t s_bar;
 
 	const int t = threadIdx.x;
 	const zn_mesh_tile tile = tiles[blockIdx.x];
-	const bool bulk = (tile.flags & 1u) != 0;
-	const uint32_t floats = tile.vertex_count * 3;
+	const bool single = !MULTI || tile.instance_lo == tile.instance_hi;
+	const uint32_t n_inst = tile.instance_hi - tile.instance_lo + 1u;
+	const bool staged = n_inst <= kMeshSmemInstances;
+	const uint32_t floats = ((tile.vertex_count + 3u) & ~3u) * 3u;   // whole 4-vertex groups: a multiple of 16 bytes
 	const size_t base = size_t(tile.first_vertex) * 3;
 
 	if (t == 0) {
 		mbar_init(&s_bar, 1);
 		fence_mbar_init();
-		if (bulk) {
-			mbar_arrive_expect_tx(&s_bar, floats * 8);
-			bulk_g2s(s_pos, pos_in + base, floats * 4, &s_bar);
-			bulk_g2s(s_nrm, nrm_in + base, floats * 4, &s_bar);
-		}
-	} else if (t == 32) {
+		mbar_arrive_expect_tx(&s_bar, floats * 8);
+		bulk_g2s(s_pos, pos_in + base, floats * 4, &s_bar);
+		bulk_g2s(s_nrm, nrm_in + base, floats * 4, &s_bar);
+	} else if (t == 32 && single) {
 		float m[16], inv[16];
-		const float4* src = reinterpret_cast<const float4*>(models + size_t(tile.instance) * 16);
+		const float4* src = reinterpret_cast<const float4*>(models + size_t(tile.instance_lo) * 16);
 #pragma unroll
 		for (int c = 0; c < 4; ++c) {
 			const float4 col = __ldg(src + c);
@@ -63,60 +111,60 @@ mesh_tile_kernel(const zn_mesh_tile* __restrict__ tiles, const float* __restrict
 			for (int c = 0; c < 3; ++c) s_nm[r * 3 + c] = inv[r * 4 + c];   // transpose(inverse)(r,c) = inverse(c,r)
 		}
 	}
-	if (!bulk) {
-		for (uint32_t k = t; k < floats; k += kMeshThreads) {
-			s_pos[k] = ld_stream(pos_in + base + k);
-			s_nrm[k] = ld_stream(nrm_in + base + k);
-		}
-	}
+	if (!single && staged)
+		for (uint32_t k = t; k <= n_inst; k += kMeshThreads) s_first[k] = __ldg(instance_first_vertex + tile.instance_lo + k);
 	__syncthreads();
-	if (bulk) mbar_wait(&s_bar, 0);
+	mbar_wait(&s_bar, 0);
 
 	if (uint32_t(t) * 4 < tile.vertex_count) {
-		float M[12], N[9];
-#pragma unroll
-		for (int k = 0; k < 12; ++k) M[k] = s_model[k];
-#pragma unroll
-		for (int k = 0; k < 9; ++k) N[k] = s_nm[k];
 		float4* pp = reinterpret_cast<float4*>(s_pos) + t * 3;
 		float4* np = reinterpret_cast<float4*>(s_nrm) + t * 3;
 		float4 a = pp[0], b = pp[1], c = pp[2];
 		float p[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
 		a = np[0]; b = np[1]; c = np[2];
 		float n[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+		float M[12], N[9];
+		if (single) {
 #pragma unroll
-		for (int v = 0; v < 4; ++v) {
-			const float px = p[3 * v], py = p[3 * v + 1], pz = p[3 * v + 2];
-			const float nx = n[3 * v], ny = n[3 * v + 1], nz = n[3 * v + 2];
-			float q[3], g[3];
+			for (int k = 0; k < 12; ++k) M[k] = s_model[k];
 #pragma unroll
-			for (int r = 0; r < 3; ++r) {
-				q[r] = add(add(add(mul(M[r * 4 + 0], px), mul(M[r * 4 + 1], py)), mul(M[r * 4 + 2], pz)), M[r * 4 + 3]);
-				g[r] = add(add(mul(N[r * 3 + 0], nx), mul(N[r * 3 + 1], ny)), mul(N[r * 3 + 2], nz));
+			for (int k = 0; k < 9; ++k) N[k] = s_nm[k];
+#pragma unroll
+			for (int v = 0; v < 4; ++v) transform_vertex(M, N, p + 3 * v, n + 3 * v);
+		} else {
+			uint32_t have = 0xFFFFFFFFu;
+#pragma unroll
+			for (int v = 0; v < 4; ++v) {
+				// instance of this vertex: the last k in [0, n_inst) with first[k] <= vertex
+				const uint32_t vertex = tile.first_vertex + uint32_t(t) * 4 + v;
+				uint32_t lo = 0, hi = n_inst - 1;
+				while (lo < hi) {
+					const uint32_t mid = (lo + hi + 1) >> 1;
+					const uint32_t f = staged ? s_first[mid] : __ldg(instance_first_vertex + tile.instance_lo + mid);
+					if (f <= vertex) lo = mid; else hi = mid - 1;
+				}
+				if (lo != have) {
+					const float4* src = reinterpret_cast<const float4*>(inst_mats + size_t(tile.instance_lo + lo) * kInstMatFloats);
+#pragma unroll
+					for (int k = 0; k < 3; ++k) { const float4 r = __ldg(src + k); M[4 * k] = r.x; M[4 * k + 1] = r.y; M[4 * k + 2] = r.z; M[4 * k + 3] = r.w; }
+					const float4 r3 = __ldg(src + 3), r4 = __ldg(src + 4);
+					const float r5 = __ldg(reinterpret_cast<const float*>(src + 5));
+					N[0] = r3.x; N[1] = r3.y; N[2] = r3.z; N[3] = r3.w; N[4] = r4.x; N[5] = r4.y; N[6] = r4.z; N[7] = r4.w; N[8] = r5;
+					have = lo;
+				}
+				transform_vertex(M, N, p + 3 * v, n + 3 * v);
 			}
-			const float len = __fsqrt_rn(add(add(mul(g[0], g[0]), mul(g[1], g[1])), mul(g[2], g[2])));
-			if (len > 0.0f) { g[0] = __fdiv_rn(g[0], len); g[1] = __fdiv_rn(g[1], len); g[2] = __fdiv_rn(g[2], len); }
-			p[3 * v] = q[0]; p[3 * v + 1] = q[1]; p[3 * v + 2] = q[2];
-			n[3 * v] = g[0]; n[3 * v + 1] = g[1]; n[3 * v + 2] = g[2];
 		}
 		pp[0] = make_float4(p[0], p[1], p[2], p[3]); pp[1] = make_float4(p[4], p[5], p[6], p[7]); pp[2] = make_float4(p[8], p[9], p[10], p[11]);
 		np[0] = make_float4(n[0], n[1], n[2], n[3]); np[1] = make_float4(n[4], n[5], n[6], n[7]); np[2] = make_float4(n[8], n[9], n[10], n[11]);
 	}
-	if (bulk) {
-		fence_proxy_async_smem();
-		__syncthreads();
-		if (t == 0) {
-			bulk_s2g(pos_out + base, s_pos, floats * 4);
-			bulk_s2g(nrm_out + base, s_nrm, floats * 4);
-			bulk_commit();
-			bulk_wait_read_all();
-		}
-	} else {
-		__syncthreads();
-		for (uint32_t k = t; k < floats; k += kMeshThreads) {
-			pos_out[base + k] = s_pos[k];
-			nrm_out[base + k] = s_nrm[k];
-		}
+	fence_proxy_async_smem();
+	__syncthreads();
+	if (t == 0) {
+		bulk_s2g(pos_out + base, s_pos, floats * 4);
+		bulk_s2g(nrm_out + base, s_nrm, floats * 4);
+		bulk_commit();
+		bulk_wait_read_all();
 	}
 }
 
@@ -176,16 +224,24 @@ int zn_mesh_create(zn_ctx* ctx, const zn_mesh_desc* desc, zn_mesh** out_mesh) {
 		ZN_REQUIRE(V % I == 0, "zn_mesh_create: vertex_count %u is not a multiple of instance_count %u", V, I);
 		for (uint32_t k = 0; k <= I; ++k) first[k] = uint32_t(uint64_t(V / I) * k);
 	}
+	// tiles of 1024 vertices over the whole stream; [instance_lo, instance_hi] = the instances a tile touches
 	std::vector<zn_mesh_tile> tiles;
-	for (uint32_t k = 0; k < I; ++k)
-		for (uint32_t v = first[k]; v < first[k + 1]; v += kMeshTileVerts) {
+	bool multi = false;
+	{
+		uint32_t k = 0;
+		for (uint32_t v = 0; v < V; v += kMeshTileVerts) {
 			zn_mesh_tile t;
 			t.first_vertex = v;
-			t.vertex_count = std::min<uint32_t>(kMeshTileVerts, first[k + 1] - v);
-			t.instance = k;
-			t.flags = (v % 4 == 0 && t.vertex_count % 4 == 0) ? 1u : 0u;
+			t.vertex_count = std::min<uint32_t>(kMeshTileVerts, V - v);
+			while (k + 1 < I && first[k + 1] <= v) ++k;                      // last instance starting at or before v
+			t.instance_lo = k;
+			uint32_t h = k;
+			while (h + 1 < I && first[h + 1] <= v + t.vertex_count - 1) ++h; // last instance starting inside the tile
+			t.instance_hi = h;
+			multi = multi || (h != k);
 			tiles.push_back(t);
 		}
+	}
 	ZN_CUDA(cudaSetDevice(ctx->device));
 	zn_mesh* m = new zn_mesh();
 	m->ctx = ctx;
@@ -195,10 +251,17 @@ int zn_mesh_create(zn_ctx* ctx, const zn_mesh_desc* desc, zn_mesh** out_mesh) {
 	auto cleanup = [&](int rc) { zn_mesh_destroy(m); return rc; };
 #define ZN_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return cleanup(fail(e_ == cudaErrorMemoryAllocation ? ZN_ERR_NOMEM : ZN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_))); } while (0)
 	ZN_TRY(cudaMalloc(&m->tiles, tiles.size() * sizeof(zn_mesh_tile)));
-	ZN_TRY(cudaMalloc(&m->pos_in, size_t(V) * 12));
-	ZN_TRY(cudaMalloc(&m->nrm_in, size_t(V) * 12));
-	ZN_TRY(cudaMalloc(&m->pos_out, size_t(V) * 12));
-	ZN_TRY(cudaMalloc(&m->nrm_out, size_t(V) * 12));
+	const size_t vpad = (size_t(V) + 3) & ~size_t(3);   // bulk copies move whole 4-vertex groups
+	ZN_TRY(cudaMalloc(&m->pos_in, vpad * 12));
+	ZN_TRY(cudaMalloc(&m->nrm_in, vpad * 12));
+	ZN_TRY(cudaMalloc(&m->pos_out, vpad * 12));
+	ZN_TRY(cudaMalloc(&m->nrm_out, vpad * 12));
+	ZN_TRY(cudaMemsetAsync(m->pos_in, 0, vpad * 12, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(m->nrm_in, 0, vpad * 12, ctx->stream));
+	ZN_TRY(cudaMalloc(&m->instance_first_vertex, (size_t(I) + 1) * 4));
+	ZN_TRY(cudaMemcpyAsync(m->instance_first_vertex, first.data(), (size_t(I) + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+	m->multi_instance_tiles = multi;
+	if (multi) ZN_TRY(cudaMalloc(&m->inst_mats, size_t(I) * kInstMatFloats * 4));
 	ZN_TRY(cudaMalloc(&m->models_own, size_t(I) * 64));
 	ZN_TRY(cudaMemcpyAsync(m->tiles, tiles.data(), tiles.size() * sizeof(zn_mesh_tile), cudaMemcpyHostToDevice, ctx->stream));
 	ZN_TRY(cudaMemsetAsync(m->models_own, 0, size_t(I) * 64, ctx->stream));
@@ -214,6 +277,7 @@ int zn_mesh_destroy(zn_mesh* m) {
 	cudaSetDevice(m->ctx->device);
 	cudaStreamSynchronize(m->ctx->stream);
 	cudaFree(m->tiles); cudaFree(m->pos_in); cudaFree(m->nrm_in); cudaFree(m->pos_out); cudaFree(m->nrm_out); cudaFree(m->models_own);
+	cudaFree(m->instance_first_vertex); cudaFree(m->inst_mats);
 	delete m;
 	return ZN_OK;
 }
@@ -252,7 +316,14 @@ int zn_mesh_bind_scene_models(zn_mesh* m, zn_scene* scene, uint32_t first_entity
 int zn_mesh_transform(zn_mesh* m) {
 	ZN_REQUIRE(m, "zn_mesh_transform: mesh is NULL");
 	ZN_CUDA(cudaSetDevice(m->ctx->device));
-	mesh_tile_kernel<<<m->tile_count, kMeshThreads, 0, m->ctx->stream>>>(m->tiles, m->models, m->pos_in, m->nrm_in, m->pos_out, m->nrm_out);
+	if (m->multi_instance_tiles)
+		mesh_instance_mats_kernel<<<(m->instance_count + 127) / 128, 128, 0, m->ctx->stream>>>(m->models, m->instance_count, m->inst_mats);
+	if (m->multi_instance_tiles)
+		mesh_tile_kernel<true><<<m->tile_count, kMeshThreads, 0, m->ctx->stream>>>(m->tiles, m->models, m->instance_first_vertex, m->inst_mats,
+		                                                                          m->pos_in, m->nrm_in, m->pos_out, m->nrm_out);
+	else
+		mesh_tile_kernel<false><<<m->tile_count, kMeshThreads, 0, m->ctx->stream>>>(m->tiles, m->models, m->instance_first_vertex, m->inst_mats,
+		                                                                           m->pos_in, m->nrm_in, m->pos_out, m->nrm_out);
 	ZN_CUDA(cudaGetLastError());
 	return ZN_OK;
 }
