@@ -305,6 +305,7 @@ def run_ours(args) -> None:
     frame_no = [0]
     use_lists = distributed and args.exchange == "lists"
     use_records = distributed and args.exchange == "records"
+    use_peer = distributed and args.exchange == "peer"
     if use_lists:
         # The exchange of the path as SURVEY §8e words it: all-gather the visible counts, then the
         # compacted index lists.  Double-buffered: the scene writes frame k's list straight into
@@ -317,6 +318,13 @@ def run_ours(args) -> None:
         # every rank expands all of them into the ordered lists (zenyth_b200.distributed.RecordExchange).
         from zenyth_b200.distributed import RecordExchange
         exchange = RecordExchange(bufs.visibility_record_words, E, world_size, dev, torch.int32, slots=2)
+        index_bases = np.asarray([(r * E) % 2 ** 32 for r in range(world_size)], np.uint32)
+    if use_peer:
+        # The same records, but no collective moves them: the level and emit kernels store every
+        # tile's mask and the record header straight into all peers' buffers over NVLink (CUDA IPC
+        # mapped peer memory); a 4-byte all-reduce per frame is the cross-rank barrier.
+        from zenyth_b200.peer_exchange import PeerRecordExchange
+        exchange = PeerRecordExchange(ctx, bufs.visibility_record_words, E, world_size, rank, dev, torch.int32, slots=4)
         index_bases = np.asarray([(r * E) % 2 ** 32 for r in range(world_size)], np.uint32)
 
     def step():
@@ -332,6 +340,13 @@ def run_ours(args) -> None:
             exchange.launch(slot)                      # all-gather of frame k: overlaps what follows
             if exchange.ready(1 - slot):               # frame k-1 has arrived: derive every rank's list
                 exchange.expand(scene, 1 - slot, index_bases)
+        elif use_peer:
+            k = frame_no[0]
+            exchange.bind(scene, k % 4)
+            scene.Update()                             # kernels write this rank's record into every peer
+            exchange.launch(k % 4)                     # barrier(k), asynchronous
+            if exchange.ready((k - 1) % 4):            # barrier(k-1) passed: all peers' frame k-1 records are here
+                exchange.expand(scene, (k - 1) % 4, index_bases)
         else:
             scene.Update()
         frame_no[0] += 1
@@ -344,6 +359,10 @@ def run_ours(args) -> None:
             for slot in ((frame_no[0] - 2) % 2, (frame_no[0] - 1) % 2):
                 if exchange.ready(slot):
                     exchange.expand(scene, slot, index_bases)
+        if use_peer:
+            for k in (frame_no[0] - 2, frame_no[0] - 1):
+                if k >= 0 and exchange.ready(k % 4):
+                    exchange.expand(scene, k % 4, index_bases)
 
     def barrier():
         if distributed:
@@ -358,9 +377,24 @@ def run_ours(args) -> None:
         scene.BindVisibleOutput(None)
         scene.Update()
     visible = scene.VisibleCount()
-    if use_records:   # every rank derived the same lists: check the count of this rank's own
+    if use_records or use_peer:   # every rank derived the same lists: check them against each rank's own count
         counts, _ = exchange.result()
-        assert counts[rank] == visible, (counts, visible)
+        own = torch.tensor([visible], dtype=torch.int32, device=dev)
+        every = torch.zeros(world_size, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(every, own)
+        assert counts == every.tolist(), (counts, every.tolist())
+        # ... and every derived list against its owner's actual list (checksums travel, not lists)
+        _, lists = exchange.result()
+        mine = torch.from_numpy(scene.Visible().astype(np.int64)).to(dev)
+
+        def checksum(t):
+            t = t.to(torch.int64) & 0xFFFFFFFF
+            return torch.stack([t.sum(), (t * (torch.arange(t.numel(), device=dev) % 1021 + 1)).sum()])
+
+        sums = torch.zeros(world_size * 2, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sums, checksum(mine))
+        for r in range(world_size):
+            assert torch.equal(checksum(lists[r, : counts[r]]), sums[2 * r: 2 * r + 2]), f"rank {rank}: list of rank {r} differs from its owner's"
 
     gpu_id = str(torch.cuda.get_device_properties(dev).uuid)
     if not gpu_id.startswith("GPU-"):
@@ -379,6 +413,8 @@ def run_ours(args) -> None:
         scene.BindVisibleOutput(None)
     if use_records:
         scene.BindVisibilityRecord(None)
+    if use_peer:
+        exchange.close(scene)
     ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -479,7 +515,10 @@ def run_ours(args) -> None:
                            ("NCCL all_gather of the fixed-size visibility records (per-chunk counts + 1 mask bit per entity) "
                             "every step, double-buffered; every rank then expands all records into the ordered index lists + "
                             "counts (identical to an all-gather of the lists, 27x fewer NVLink bytes); the timed region "
-                            "ends after the last expansion; --exchange lists runs the literal list all-gather") if use_records
+                            "ends after the last expansion; --exchange lists runs the literal list all-gather") if use_records else
+                           ("fused into the compute kernels over NVLink peer memory: the level and emit kernels store the visibility "
+                            "record tile by tile into every peer's buffer (CUDA IPC mapped pointers); a 4-byte NCCL all-reduce per "
+                            "frame is the cross-rank barrier; every rank expands all records into the ordered index lists + counts") if use_peer
                            else "none (1 GPU)")},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -684,8 +723,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["mesh64m", "scenes8x32m"], default="h8geo16m")
-    ap.add_argument("--exchange", choices=["records", "lists"], default="records",
-                    help="N>1: all-gather visibility records and expand locally (default), or all-gather the index lists")
+    ap.add_argument("--exchange", choices=["records", "lists", "peer"], default="records",
+                    help="N>1: all-gather visibility records and expand locally (default); all-gather the index lists; or let the "
+                         "kernels store the records straight into peer GPUs' memory over NVLink")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     args = ap.parse_args()

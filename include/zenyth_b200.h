@@ -64,6 +64,15 @@ int zn_ctx_sm_count(zn_ctx* ctx, int* out_sm_count);
 /* Page-locked host memory for the *_host entry points (plain malloc memory also works, slower). */
 int zn_host_alloc(zn_ctx* ctx, size_t bytes, void** out_ptr);
 int zn_host_free(zn_ctx* ctx, void* ptr);
+/* Peer memory (one process per GPU): a plain device allocation, its 64-byte CUDA IPC handle, and
+ * the mapping of another rank's handle into this process (peer access over NVLink is enabled
+ * lazily).  The handle bytes travel between ranks by any host channel (torch.distributed,
+ * MPI, a pipe). */
+int zn_device_alloc(zn_ctx* ctx, size_t bytes, void** out_ptr);
+int zn_device_free(zn_ctx* ctx, void* ptr);
+int zn_ipc_export(zn_ctx* ctx, void* dev_ptr, unsigned char out_handle[64]);
+int zn_ipc_open(zn_ctx* ctx, const unsigned char handle[64], void** out_dev_ptr);
+int zn_ipc_close(zn_ctx* ctx, void* dev_ptr);
 
 /* ---- camera maths: the part of mat4 a Camera needs, completing the stubs
  *      mat4::look_at / perspective / orthographic / perspective_reverse_z / operator*
@@ -121,6 +130,11 @@ int zn_scene_bind_visible_output(zn_scene* scene, void* visible_dev, uint32_t ca
  *     counts_dev[r]; index_bases[r] (host array, may be NULL) is added to record r's indices;
  *     record `skip_index` is left out (-1: none).  Asynchronous on the context stream. */
 int zn_scene_bind_visibility_record(zn_scene* scene, void* record_dev);
+/* Fused all-gather over peer memory: every update also stores the record, tile by tile from
+ * inside the compute kernels, into up to 7 additional buffers — device pointers into PEER GPUs'
+ * memory, mapped through zn_ipc_open (NVLink P2P) — so after a cross-rank barrier every rank holds
+ * every rank's record without a collective having moved it.  peer_count == 0 unbinds. */
+int zn_scene_bind_peer_records(zn_scene* scene, void* const* peer_record_ptrs, uint32_t peer_count);
 int zn_scene_expand_visible(zn_scene* scene, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
                             int skip_index, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev);
 /* Added to every index written to the visible list (shard -> global numbering). */

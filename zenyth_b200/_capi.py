@@ -59,6 +59,11 @@ PROTOTYPES = {
     "zn_ctx_sm_count": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "zn_host_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "zn_host_free": (C.c_int, [vp, vp]),
+    "zn_device_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "zn_device_free": (C.c_int, [vp, vp]),
+    "zn_ipc_export": (C.c_int, [vp, vp, vp]),
+    "zn_ipc_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "zn_ipc_close": (C.c_int, [vp, vp]),
     "zn_mat4_look_at": (None, [vp, vp, vp, vp]),
     "zn_mat4_perspective": (None, [C.c_float, C.c_float, C.c_float, C.c_float, vp]),
     "zn_mat4_orthographic": (None, [C.c_float] * 6 + [vp]),
@@ -73,6 +78,7 @@ PROTOTYPES = {
     "zn_scene_set_camera": (C.c_int, [vp, vp, vp]),
     "zn_scene_bind_visible_output": (C.c_int, [vp, vp, C.c_uint32, vp]),
     "zn_scene_bind_visibility_record": (C.c_int, [vp, vp]),
+    "zn_scene_bind_peer_records": (C.c_int, [vp, vp, C.c_uint32]),
     "zn_scene_expand_visible": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, C.c_uint32, vp]),
     "zn_scene_set_index_base": (C.c_int, [vp, C.c_uint32]),
     "zn_scene_update": (C.c_int, [vp]),

@@ -148,4 +148,47 @@ int zn_host_free(zn_ctx* ctx, void* ptr) {
 	return ZN_OK;
 }
 
+// ---- peer memory: device allocations that other ranks (processes) of the node can map ----------
+int zn_device_alloc(zn_ctx* ctx, size_t bytes, void** out_ptr) {
+	ZN_REQUIRE(ctx && out_ptr, "zn_device_alloc: NULL argument");
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	ZN_CUDA(cudaMalloc(out_ptr, bytes ? bytes : 1));
+	ZN_CUDA(cudaMemsetAsync(*out_ptr, 0, bytes ? bytes : 1, ctx->stream));
+	ZN_CUDA(cudaStreamSynchronize(ctx->stream));
+	return ZN_OK;
+}
+
+int zn_device_free(zn_ctx* ctx, void* ptr) {
+	ZN_REQUIRE(ctx, "zn_device_free: ctx is NULL");
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	if (ptr) ZN_CUDA(cudaFree(ptr));
+	return ZN_OK;
+}
+
+int zn_ipc_export(zn_ctx* ctx, void* dev_ptr, unsigned char out_handle[64]) {
+	ZN_REQUIRE(ctx && dev_ptr && out_handle, "zn_ipc_export: NULL argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	ZN_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+	memcpy(out_handle, &h, 64);
+	return ZN_OK;
+}
+
+int zn_ipc_open(zn_ctx* ctx, const unsigned char handle[64], void** out_dev_ptr) {
+	ZN_REQUIRE(ctx && handle && out_dev_ptr, "zn_ipc_open: NULL argument");
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	ZN_CUDA(cudaIpcOpenMemHandle(out_dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return ZN_OK;
+}
+
+int zn_ipc_close(zn_ctx* ctx, void* dev_ptr) {
+	ZN_REQUIRE(ctx, "zn_ipc_close: ctx is NULL");
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	if (dev_ptr) ZN_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+	return ZN_OK;
+}
+
 } // extern "C"

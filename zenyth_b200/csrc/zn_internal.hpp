@@ -83,6 +83,7 @@ struct zn_scene {
 	uint32_t* record = nullptr;            // where the kernels write (own buffer or a bound one)
 	uint32_t* record_own = nullptr;
 	uint32_t record_words = 0;
+	std::vector<uint32_t*> peer_records;   // copies of the record kept by peer GPUs (mapped device pointers), written by the kernels
 	uint32_t* tile_first_entity = nullptr; // [tiles]
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
 	uint32_t* chunk_total = nullptr;       // [2][chunks] visible count per chunk, one set per frame parity

@@ -267,6 +267,18 @@ int zn_scene_bind_visibility_record(zn_scene* s, void* record_dev) {
 	return ZN_OK;
 }
 
+int zn_scene_bind_peer_records(zn_scene* s, void* const* peer_record_ptrs, uint32_t peer_count) {
+	ZN_REQUIRE(s, "zn_scene_bind_peer_records: scene is NULL");
+	ZN_REQUIRE(peer_count < uint32_t(kMaxRecordTargets), "zn_scene_bind_peer_records: at most %d peers", kMaxRecordTargets - 1);
+	ZN_REQUIRE(peer_record_ptrs || peer_count == 0, "zn_scene_bind_peer_records: NULL pointer array");
+	s->peer_records.clear();
+	for (uint32_t k = 0; k < peer_count; ++k) {
+		ZN_REQUIRE(peer_record_ptrs[k], "zn_scene_bind_peer_records: peer %u is NULL", k);
+		s->peer_records.push_back(static_cast<uint32_t*>(peer_record_ptrs[k]));
+	}
+	return ZN_OK;
+}
+
 int zn_scene_expand_visible(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
                             const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev) {
 	ZN_REQUIRE(s && records_dev && lists_dev && counts_dev, "zn_scene_expand_visible: NULL argument");
@@ -303,6 +315,11 @@ int zn_scene_update(zn_scene* s) {
 	std::memcpy(fc.vp, s->view_proj, sizeof(fc.vp));
 	std::memcpy(fc.planes, s->planes, sizeof(fc.planes));
 	const bool prof = s->profiling;
+	RecordTargets rec = {};
+	rec.ptr[0] = s->record;
+	rec.n = 1;
+	for (uint32_t* peer : s->peer_records) rec.ptr[rec.n++] = peer;
+	const uint32_t header_words = record_header_words(s->chunk_count);
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
 	uint32_t* totals_next = s->chunk_total + size_t(s->frame_parity ^ 1u) * s->chunk_count;
 	s->frame_parity ^= 1u;
@@ -328,11 +345,11 @@ int zn_scene_update(zn_scene* s) {
 		if (l == 0)
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<false>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           s->record + record_header_words(s->chunk_count), totals, ticket, lv.ticket_base));
+			                           rec, header_words, totals, ticket, lv.ticket_base));
 		else
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<true>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           s->record + record_header_words(s->chunk_count), totals, ticket, lv.ticket_base));
+			                           rec, header_words, totals, ticket, lv.ticket_base));
 		// every tile takes one ticket and every CTA one more (the draw that tells it to stop)
 		lv.ticket_base += lv.tiles + grid;
 	}
@@ -341,7 +358,7 @@ int zn_scene_update(zn_scene* s) {
 	cfg.blockDim = dim3(256);
 	cfg.dynamicSmemBytes = 0;
 	cfg.numAttrs = prof ? 0 : 1;
-	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, s->record, (const uint32_t*)s->tile_first_entity,
+	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, rec, (const uint32_t*)s->tile_first_entity,
 	                           s->tile_count, s->chunk_count, (const uint32_t*)totals, totals_next, s->index_base, s->visible, s->visible_count));
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
 	return ZN_OK;

@@ -50,13 +50,23 @@ constexpr uint32_t kLevelSmem = kOutBytes + kInBytes + kParBytes + 1024;
 constexpr uint32_t kGather = 0xFFFFFFFFu;                  // tile_prange.y: parents too scattered to stage
 constexpr int kChunkTiles = 32;                            // tiles per emit CTA (8192 entities)
 
+// Where a frame's visibility record is written: ptr[0] is this rank's own copy; ptr[1..n) are the
+// copies kept by peer GPUs (device pointers into their memory, mapped over NVLink through CUDA
+// IPC).  The kernels store to all of them, which fuses the all-gather of the records into the
+// compute kernels tile by tile.
+constexpr int kMaxRecordTargets = 8;
+struct RecordTargets {
+	uint32_t* ptr[kMaxRecordTargets];
+	int n;
+};
+
 template <bool HAS_PARENT>
 __global__ void __launch_bounds__(kTile, 4)
 scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_constant__ CUtensorMap tm_mvp,
                    const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
                    const uint2* __restrict__ tile_prange, const float* __restrict__ world_rd,
                    uint32_t begin, uint32_t end, uint32_t tile_base, uint32_t tiles,
-                   uint32_t* __restrict__ tile_mask, uint32_t* __restrict__ chunk_total,
+                   const __grid_constant__ RecordTargets rec, uint32_t header_words, uint32_t* __restrict__ chunk_total,
                    uint32_t* __restrict__ ticket, uint32_t ticket_base) {
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ uint64_t s_full;
@@ -175,9 +185,16 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		if (warp == 0) {
 			const uint32_t gt = tile_base + tl;
 			const uint32_t word = (lane < kWarpsPerTile) ? s_mask[lane] : 0u;
-			if (lane < kWarpsPerTile) tile_mask[size_t(gt) * kWarpsPerTile + lane] = word;
+			if (lane < kWarpsPerTile) rec.ptr[0][header_words + size_t(gt) * kWarpsPerTile + lane] = word;
 			const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(word));
 			if (lane == 0) atomicAdd(chunk_total + gt / kChunkTiles, cnt);
+		} else if (warp == kWarpsPerTile - 1 && rec.n > 1 && lane < kWarpsPerTile) {
+			// ... and, over NVLink, straight into the copy of this rank's record that every peer keeps
+			// (fused all-gather: plain stores to mapped peer memory).  Issued by the last warp so the
+			// TMA-issuing warp never queues behind remote stores.
+			const uint32_t word = s_mask[lane];
+			const size_t at = header_words + size_t(tile_base + tl) * kWarpsPerTile + lane;
+			for (int q = 1; q < rec.n; ++q) rec.ptr[q][at] = word;
 		}
 	}
 	if (t == 0) bulk_wait_read_all();
@@ -238,7 +255,7 @@ __device__ __forceinline__ void scatter_warp_words(const uint4* __restrict__ w4,
 __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ totals, const uint32_t* __restrict__ masks,
                                                const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t chunks,
                                                uint32_t chunk, uint32_t index_base, uint32_t* __restrict__ visible,
-                                               uint32_t* __restrict__ visible_count, uint32_t* __restrict__ record_out) {
+                                               uint32_t* __restrict__ visible_count, const RecordTargets& record_out) {
 	__shared__ uint32_t s_part[8];
 	__shared__ uint32_t s_warp_excl[8];
 	__shared__ uint32_t s_base, s_total;
@@ -273,15 +290,15 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 		const uint32_t total = __shfl_sync(0xffffffffu, winc, 7);
 		if (lane < 8) {
 			s_warp_excl[lane] = winc - wt;
-			record_out[chunks + 1u + chunk * 8u + lane] = winc - wt;
+			for (int q = 0; q < record_out.n; ++q) record_out.ptr[q][chunks + 1u + chunk * 8u + lane] = winc - wt;
 		}
 		if (lane == 0) {
 			s_base = base;
 			s_total = total;
-			record_out[chunk] = base;
+			for (int q = 0; q < record_out.n; ++q) record_out.ptr[q][chunk] = base;
 			if (chunk == chunks - 1) {
 				*visible_count = base + total;
-				record_out[chunks] = base + total;
+				for (int q = 0; q < record_out.n; ++q) record_out.ptr[q][chunks] = base + total;
 			}
 		}
 	}
@@ -313,12 +330,13 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 // every CTA clears its own entry of the OTHER set (last read by the previous frame's emit), so the
 // next frame finds zeros without any cross-CTA handshake.
 __global__ void __launch_bounds__(256)
-emit_visible_kernel(uint32_t* __restrict__ record, const uint32_t* __restrict__ tile_first_entity,
+emit_visible_kernel(const __grid_constant__ RecordTargets rec, const uint32_t* __restrict__ tile_first_entity,
                     uint32_t tiles, uint32_t chunks, const uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ chunk_total_next,
                     uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
 	const uint32_t chunk = blockIdx.x;
 	grid_dep_wait();   // masks and totals of every level are complete and visible
-	emit_chunk(chunk_total, record + record_header_words(chunks), tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count, record);
+	// rec.ptr[0] is this rank's own record (the masks are read from it); the header goes to all targets
+	emit_chunk(chunk_total, rec.ptr[0] + record_header_words(chunks), tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count, rec);
 	if (threadIdx.x == 0) chunk_total_next[chunk] = 0u;
 }
 

@@ -104,6 +104,30 @@ class GpuContext:
         buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    # -- peer memory (multi-GPU, one process per GPU) -------------------------------------------
+    def DeviceAlloc(self, nbytes: int) -> int:
+        """A zero-filled device allocation other ranks can map (zn_device_alloc); returns the pointer."""
+        ptr = C.c_void_p()
+        check(self._lib.zn_device_alloc(self._h, nbytes, C.byref(ptr)))
+        return int(ptr.value)
+
+    def DeviceFree(self, ptr: int) -> None:
+        check(self._lib.zn_device_free(self._h, C.c_void_p(ptr)))
+
+    def IpcExport(self, ptr: int) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        check(self._lib.zn_ipc_export(self._h, C.c_void_p(ptr), buf))
+        return bytes(buf)
+
+    def IpcOpen(self, handle: bytes) -> int:
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        ptr = C.c_void_p()
+        check(self._lib.zn_ipc_open(self._h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def IpcClose(self, ptr: int) -> None:
+        check(self._lib.zn_ipc_close(self._h, C.c_void_p(ptr)))
+
     def Close(self) -> None:
         if getattr(self, "_h", None):
             for ptr in getattr(self, "_pinned", []):
@@ -217,6 +241,12 @@ class Scene:
     def BindVisibilityRecord(self, record_ptr: int | None) -> None:
         """Subsequent updates write the frame's visibility record into caller-owned device memory."""
         check(self._lib.zn_scene_bind_visibility_record(self._h, C.c_void_p(record_ptr or 0)))
+
+    def BindPeerRecords(self, peer_ptrs) -> None:
+        """Every update also stores the visibility record into these mapped PEER-GPU buffers."""
+        peer_ptrs = list(peer_ptrs)
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
+        check(self._lib.zn_scene_bind_peer_records(self._h, arr, len(peer_ptrs)))
 
     def ExpandVisible(self, records_ptr: int, record_count: int, record_stride_words: int, lists_ptr: int, list_stride: int,
                       counts_ptr: int, index_bases=None, skip_index: int = -1) -> None:
