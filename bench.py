@@ -305,7 +305,7 @@ def run_ours(args) -> None:
     frame_no = [0]
     use_lists = distributed and args.exchange == "lists"
     use_records = distributed and args.exchange == "records"
-    use_peer = distributed and args.exchange == "peer"
+    use_peer = distributed and args.exchange in ("peer", "peer-nccl", "peer-waitkernel")
     if use_lists:
         # The exchange of the path as SURVEY §8e words it: all-gather the visible counts, then the
         # compacted index lists.  Double-buffered: the scene writes frame k's list straight into
@@ -322,9 +322,13 @@ def run_ours(args) -> None:
     if use_peer:
         # The same records, but no collective moves them: the level and emit kernels store every
         # tile's mask and the record header straight into all peers' buffers over NVLink (CUDA IPC
-        # mapped peer memory); a 4-byte all-reduce per frame is the cross-rank barrier.
+        # mapped peer memory); the emit kernel's last CTA raises a flag at every peer and the
+        # expansion kernel waits on those flags itself ("peer-nccl": a 4-byte all-reduce per frame
+        # is the cross-rank barrier instead).
         from zenyth_b200.peer_exchange import PeerRecordExchange
-        exchange = PeerRecordExchange(ctx, bufs.visibility_record_words, E, world_size, rank, dev, torch.int32, slots=4)
+        exchange = PeerRecordExchange(ctx, bufs.visibility_record_words, E, world_size, rank, dev, torch.int32, slots=4,
+                                      signal="nccl" if args.exchange == "peer-nccl" else "flags",
+                                      fused_wait=args.exchange != "peer-waitkernel")
         index_bases = np.asarray([(r * E) % 2 ** 32 for r in range(world_size)], np.uint32)
 
     def step():
@@ -342,11 +346,10 @@ def run_ours(args) -> None:
                 exchange.expand(scene, 1 - slot, index_bases)
         elif use_peer:
             k = frame_no[0]
-            exchange.bind(scene, k % 4)
-            scene.Update()                             # kernels write this rank's record into every peer
-            exchange.launch(k % 4)                     # barrier(k), asynchronous
-            if exchange.ready((k - 1) % 4):            # barrier(k-1) passed: all peers' frame k-1 records are here
-                exchange.expand(scene, (k - 1) % 4, index_bases)
+            exchange.bind(scene, k)
+            scene.Update()                             # kernels write this rank's record into every peer, then signal
+            exchange.launch(k)                         # (peer-nccl only: barrier(k), asynchronous)
+            exchange.expand(scene, k - 1, index_bases)   # waits on the device for the peers' frame k-1 signals
         else:
             scene.Update()
         frame_no[0] += 1
@@ -361,8 +364,7 @@ def run_ours(args) -> None:
                     exchange.expand(scene, slot, index_bases)
         if use_peer:
             for k in (frame_no[0] - 2, frame_no[0] - 1):
-                if k >= 0 and exchange.ready(k % 4):
-                    exchange.expand(scene, k % 4, index_bases)
+                exchange.expand(scene, k, index_bases)
 
     def barrier():
         if distributed:
@@ -516,9 +518,13 @@ def run_ours(args) -> None:
                             "every step, double-buffered; every rank then expands all records into the ordered index lists + "
                             "counts (identical to an all-gather of the lists, 27x fewer NVLink bytes); the timed region "
                             "ends after the last expansion; --exchange lists runs the literal list all-gather") if use_records else
-                           ("fused into the compute kernels over NVLink peer memory: the level and emit kernels store the visibility "
-                            "record tile by tile into every peer's buffer (CUDA IPC mapped pointers); a 4-byte NCCL all-reduce per "
-                            "frame is the cross-rank barrier; every rank expands all records into the ordered index lists + counts") if use_peer
+                           ("fused into the compute kernels over NVLink peer memory, no collective: the level and emit kernels store "
+                            "the visibility record tile by tile into every peer's buffer (CUDA IPC mapped pointers); "
+                            + ("the emit kernel's last CTA raises a sequence flag at every peer (fence.sys + st.release.sys) and the "
+                               "expansion kernel waits on the owners' flags itself — no NCCL call in the timed region; "
+                               if args.exchange != "peer-nccl" else "a 4-byte NCCL all-reduce per frame is the cross-rank barrier; ")
+                            + "every rank expands its peers' records into the ordered index lists + counts (its own list comes "
+                              "straight from its emit kernel)") if use_peer
                            else "none (1 GPU)")},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -532,7 +538,7 @@ def run_ours(args) -> None:
                                    "profiled_frame_ms": frame_ms_prof}},
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": args.steps * launches_per_update,
+            "gpu_launches": args.steps * (launches_per_update + (1 if (use_records or use_peer) else 0)),
         }
         emit_line(json.dumps(line), flush=True)
     scene.Close()
@@ -723,9 +729,10 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["mesh64m", "scenes8x32m"], default="h8geo16m")
-    ap.add_argument("--exchange", choices=["records", "lists", "peer"], default="records",
-                    help="N>1: all-gather visibility records and expand locally (default); all-gather the index lists; or let the "
-                         "kernels store the records straight into peer GPUs' memory over NVLink")
+    ap.add_argument("--exchange", choices=["records", "lists", "peer", "peer-nccl", "peer-waitkernel"], default="records",
+                    help="N>1: all-gather visibility records and expand locally (records); all-gather the index lists (lists); or let "
+                         "the kernels store the records straight into peer GPUs' memory over NVLink and signal completion with "
+                         "flags in peer memory (peer) or a 4-byte all-reduce (peer-nccl)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     args = ap.parse_args()

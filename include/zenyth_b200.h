@@ -137,6 +137,27 @@ int zn_scene_bind_visibility_record(zn_scene* scene, void* record_dev);
 int zn_scene_bind_peer_records(zn_scene* scene, void* const* peer_record_ptrs, uint32_t peer_count);
 int zn_scene_expand_visible(zn_scene* scene, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
                             int skip_index, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev);
+/* The cross-rank completion signal of that fused all-gather, again without a collective.
+ *   bind_peer_signal: flag_ptrs[q] is ONE 32-bit word in rank q's memory (this rank's cell of q's flag
+ *     array; mapped through zn_ipc_open, the own cell is a plain local pointer).  flag_count == 0 unbinds.
+ *   set_signal_value: the sequence number of the latest update enqueued on the stream; it only grows
+ *     (compared as a signed 32-bit distance, so it may wrap).
+ *   expand_visible_signalled: zn_scene_expand_visible that (1) first raises the bound flags to the
+ *     signal value — every update enqueued before it is complete by then, peer stores included
+ *     (fence.sys + st.release.sys by one thread) — and (2) whose CTAs wait (ld.acquire.sys) until
+ *     flags_dev[(r / records_per_flag) * flag_stride_words] has reached `expected` for their record
+ *     r, so the stream needs no host- or NCCL-side barrier.  The wait is bounded: after timeout_ms
+ *     the kernel stores 1 + r into *status_dev (a zero-initialised device word) and goes on. */
+int zn_scene_bind_peer_signal(zn_scene* scene, void* const* flag_ptrs, uint32_t flag_count);
+/* The same signal + bounded wait as a launch of its own on the context stream (all flag_count
+ * flags must reach `expected`); a plain zn_scene_expand_visible may follow it. */
+int zn_scene_wait_flags(zn_scene* scene, const void* flags_dev, uint32_t flag_stride_words, uint32_t flag_count, uint32_t expected,
+                        uint32_t timeout_ms, void* status_dev);
+int zn_scene_set_signal_value(zn_scene* scene, uint32_t value);
+int zn_scene_expand_visible_signalled(zn_scene* scene, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
+                                      int skip_index, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
+                                      const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
+                                      uint32_t timeout_ms, void* status_dev);
 /* Added to every index written to the visible list (shard -> global numbering). */
 int zn_scene_set_index_base(zn_scene* scene, uint32_t index_base);
 

@@ -1,0 +1,165 @@
+"""The collective-free exchange: records stored into extra ("peer") buffers by the kernels, the
+completion flag raised by the emit kernel, the flag-gated expansion.  On one GPU the "peers" are
+further local buffers, which exercises exactly the same kernels and entry points; the two-process
+test over real CUDA IPC / NVLink runs where two GPUs are visible (bench.py --exchange peer checks
+the same thing at N = 2..8 at full size)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle.binding import BASE_SEED, camera, h8_geo_level_sizes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _scene(oracle, gpu_ctx, levels=5):
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, levels)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    view, proj = camera(oracle)
+    sc = zn.Scene(gpu_ctx, sum(sizes), arrays["level_offsets"])
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    return sc, sum(sizes), oracle.scene_update(arrays, view, proj)["visible"]
+
+
+def _big_scene(gpu_ctx):
+    """7 levels, the last one 1.8M entities: above the size from which a level kernel pushes its own masks."""
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 7)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    sc = zn.Scene(gpu_ctx, sum(sizes), offs)
+    sc.FillSynthetic(BASE_SEED + 3, 8, 0.25)
+    sc.SetCamera(zn.Camera(zn.CameraDesc(eye=(0.0, 0.0, 1500.0), center=(0.0, 0.0, 1499.0))))
+    sc.Update()
+    return sc, sum(sizes), sc.Visible()      # the plain path is checked against the oracle elsewhere
+
+
+@pytest.mark.parametrize("big", [False, True], ids=["small-levels-only", "with-a-big-level"])
+def test_kernels_store_the_record_into_every_target_and_signal(oracle, gpu_ctx, big):
+    import torch
+    sc, E, expect = _big_scene(gpu_ctx) if big else _scene(oracle, gpu_ctx)
+    assert 0 < expect.size < E
+    words = sc.DeviceBuffers().visibility_record_words
+    recs = torch.zeros(4 * words, dtype=torch.int32, device="cuda")          # own + 3 "peers"
+    flags = torch.zeros(4 * 32, dtype=torch.int32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lists = torch.full((4 * E,), -1, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(4, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    base, fbase = recs.data_ptr(), flags.data_ptr()
+    sc.BindVisibilityRecord(base + 4 * words)                                 # own copy = record 1
+    sc.BindPeerRecords([base, base + 8 * words, base + 12 * words])
+    sc.BindPeerSignal([fbase + 128 * r for r in range(4)])
+    for frame in range(3):                                                    # the done-counter resets every frame
+        sc.SetSignalValue(frame + 1)
+        sc.Update()
+        sc.ExpandVisibleSignalled(base, 4, words, lists.data_ptr(), E, counts.data_ptr(), fbase, 32, frame + 1, status.data_ptr(),
+                                  index_bases=[0, 0, 7, 0], timeout_ms=5000)
+        gpu_ctx.Sync()
+        assert status.item() == 0
+        assert flags.view(4, 32)[:, 0].tolist() == [frame + 1] * 4
+    got_recs = recs.view(4, words).cpu().numpy()
+    for r in (0, 2, 3):
+        assert np.array_equal(got_recs[r], got_recs[1]), f"target {r} differs from the own record"
+    assert np.array_equal(sc.Visible(), expect)
+    assert counts.tolist() == [expect.size] * 4
+    got = lists.view(4, E).cpu().numpy()
+    for r in range(4):
+        assert np.array_equal(got[r, :expect.size], expect.astype(np.int32) + (7 if r == 2 else 0))
+    sc.BindPeerRecords([])
+    sc.BindPeerSignal([])
+    sc.BindVisibilityRecord(None)
+    sc.Update()
+    assert np.array_equal(sc.Visible(), expect)
+    sc.Close()
+
+
+def test_a_signal_that_never_comes_times_out_instead_of_hanging(oracle, gpu_ctx):
+    import torch
+    sc, E, expect = _scene(oracle, gpu_ctx, levels=3)
+    words = sc.DeviceBuffers().visibility_record_words
+    recs = torch.zeros(2 * words, dtype=torch.int32, device="cuda")
+    flags = torch.zeros(2 * 32, dtype=torch.int32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lists = torch.zeros(2 * E, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(2, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    sc.BindVisibilityRecord(recs.data_ptr())
+    sc.BindPeerSignal([flags.data_ptr()])                                     # only "rank 0" ever signals
+    sc.SetSignalValue(1)
+    sc.Update()
+    sc.ExpandVisibleSignalled(recs.data_ptr(), 2, words, lists.data_ptr(), E, counts.data_ptr(), flags.data_ptr(), 32, 1,
+                              status.data_ptr(), timeout_ms=20)
+    gpu_ctx.Sync()
+    assert status.item() == 2                                                 # 1 + the silent rank
+    assert counts[0].item() == expect.size
+    # a flag already AHEAD of the expected sequence number passes at once
+    flags[32] = 5
+    status.zero_()
+    torch.cuda.synchronize()
+    sc.ExpandVisibleSignalled(recs.data_ptr(), 2, words, lists.data_ptr(), E, counts.data_ptr(), flags.data_ptr(), 32, 1,
+                              status.data_ptr(), skip_index=0, timeout_ms=20)
+    gpu_ctx.Sync()
+    assert status.item() == 0
+    sc.BindPeerSignal([])
+    sc.BindVisibilityRecord(None)
+    sc.Close()
+
+
+_TWO_RANKS = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ZN_ROOT"])
+import zenyth_b200 as zn
+from zenyth_b200.peer_exchange import PeerRecordExchange
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
+ctx = zn.GpuContext(rank, stream=stream.cuda_stream)
+sizes = [7 * 8 ** l for l in range(7)]
+E = sum(sizes)
+offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+for signal in ("flags", "nccl"):
+    sc = zn.Scene(ctx, E, offs)
+    sc.FillSynthetic(0x5A454E59 + 11 + rank, 8, 0.25)
+    sc.SetCamera(zn.Camera(zn.CameraDesc(eye=(0, 0, 1500.0), center=(0, 0, 1499.0))))
+    sc.SetIndexBase(rank * E)
+    sc.Update()
+    mine = sc.Visible().astype(np.int64)
+    ex = PeerRecordExchange(ctx, sc.DeviceBuffers().visibility_record_words, E, world, rank, dev, torch.int32, signal=signal)
+    bases = np.arange(world, dtype=np.uint32) * E
+    for k in range(9):
+        ex.bind(sc, k); sc.Update(); ex.launch(k); ex.expand(sc, k - 1, bases)
+    ex.expand(sc, 8, bases)
+    counts, lists = ex.result()
+    every = [None] * world
+    dist.all_gather_object(every, mine)
+    for r in range(world):
+        assert counts[r] == every[r].size, (signal, r, counts, every[r].size)
+        assert np.array_equal(lists[r, :counts[r]].cpu().numpy().astype(np.int64) & 0xFFFFFFFF, every[r]), (signal, r)
+    ex.close(sc)
+    sc.Close()
+ctx.Close()
+dist.destroy_process_group()
+print("peer exchange ok", rank)
+"""
+
+
+def test_two_processes_exchange_over_peer_memory(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (covered at N = 2..8 by bench.py --exchange peer)")
+    script = tmp_path / "two_ranks.py"
+    script.write_text(_TWO_RANKS)
+    env = dict(os.environ, ZN_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29731", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("peer exchange ok") == 2

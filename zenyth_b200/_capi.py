@@ -80,6 +80,11 @@ PROTOTYPES = {
     "zn_scene_bind_visibility_record": (C.c_int, [vp, vp]),
     "zn_scene_bind_peer_records": (C.c_int, [vp, vp, C.c_uint32]),
     "zn_scene_expand_visible": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, C.c_uint32, vp]),
+    "zn_scene_bind_peer_signal": (C.c_int, [vp, vp, C.c_uint32]),
+    "zn_scene_wait_flags": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+    "zn_scene_set_signal_value": (C.c_int, [vp, C.c_uint32]),
+    "zn_scene_expand_visible_signalled": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, C.c_uint32, vp,
+                                                    vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
     "zn_scene_set_index_base": (C.c_int, [vp, C.c_uint32]),
     "zn_scene_update": (C.c_int, [vp]),
     "zn_scene_visible_count": (C.c_int, [vp, c_u32_p]),

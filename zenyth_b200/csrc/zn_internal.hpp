@@ -84,6 +84,8 @@ struct zn_scene {
 	uint32_t* record_own = nullptr;
 	uint32_t record_words = 0;
 	std::vector<uint32_t*> peer_records;   // copies of the record kept by peer GPUs (mapped device pointers), written by the kernels
+	std::vector<uint32_t*> peer_flags;     // one flag word per rank (own included), raised to signal_value by zn_scene_expand_visible_signalled
+	uint32_t signal_value = 0;
 	uint32_t* tile_first_entity = nullptr; // [tiles]
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
 	uint32_t* chunk_total = nullptr;       // [2][chunks] visible count per chunk, one set per frame parity

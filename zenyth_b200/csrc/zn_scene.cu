@@ -279,18 +279,75 @@ int zn_scene_bind_peer_records(zn_scene* s, void* const* peer_record_ptrs, uint3
 	return ZN_OK;
 }
 
-int zn_scene_expand_visible(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
-                            const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev) {
-	ZN_REQUIRE(s && records_dev && lists_dev && counts_dev, "zn_scene_expand_visible: NULL argument");
-	ZN_REQUIRE(record_count >= 1 && record_count <= 64, "zn_scene_expand_visible: record_count %u must be in [1, 64]", record_count);
-	ZN_REQUIRE(record_stride_words >= s->record_words, "zn_scene_expand_visible: record stride %u < record size %u words", record_stride_words, s->record_words);
-	ZN_REQUIRE(list_stride >= s->entity_count, "zn_scene_expand_visible: list stride %u < entity_count %u", list_stride, s->entity_count);
+int zn_scene_bind_peer_signal(zn_scene* s, void* const* flag_ptrs, uint32_t flag_count) {
+	ZN_REQUIRE(s, "zn_scene_bind_peer_signal: scene is NULL");
+	ZN_REQUIRE(flag_count <= uint32_t(kMaxRecordTargets), "zn_scene_bind_peer_signal: at most %d flags", kMaxRecordTargets);
+	ZN_REQUIRE(flag_ptrs || flag_count == 0, "zn_scene_bind_peer_signal: NULL pointer array");
+	s->peer_flags.clear();
+	for (uint32_t k = 0; k < flag_count; ++k) {
+		ZN_REQUIRE(flag_ptrs[k] && reinterpret_cast<uintptr_t>(flag_ptrs[k]) % 4 == 0, "zn_scene_bind_peer_signal: flag %u is NULL or misaligned", k);
+		s->peer_flags.push_back(static_cast<uint32_t*>(flag_ptrs[k]));
+	}
+	return ZN_OK;
+}
+
+int zn_scene_set_signal_value(zn_scene* s, uint32_t value) {
+	ZN_REQUIRE(s, "zn_scene_set_signal_value: scene is NULL");
+	s->signal_value = value;
+	return ZN_OK;
+}
+
+static int expand_visible(zn_scene* s, const char* who, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
+                          int skip_index, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
+                          const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
+                          uint32_t timeout_ms, void* status_dev) {
+	ZN_REQUIRE(s && records_dev && lists_dev && counts_dev, "%s: NULL argument", who);
+	ZN_REQUIRE(record_count >= 1 && record_count <= 64, "%s: record_count %u must be in [1, 64]", who, record_count);
+	ZN_REQUIRE(record_stride_words >= s->record_words, "%s: record stride %u < record size %u words", who, record_stride_words, s->record_words);
+	ZN_REQUIRE(list_stride >= s->entity_count, "%s: list stride %u < entity_count %u", who, list_stride, s->entity_count);
 	ZN_CUDA(cudaSetDevice(s->ctx->device));
 	ExpandBases bases;
 	for (uint32_t r = 0; r < 64; ++r) bases.base[r] = (index_bases && r < record_count) ? index_bases[r] : 0u;
+	SignalTargets sig = {};
+	if (flags_dev) {   // the signalled form also raises this rank's own flags: everything before it on the stream is complete
+		for (uint32_t* flag : s->peer_flags) sig.flag[sig.n++] = flag;
+		sig.value = s->signal_value;
+	}
 	expand_visible_kernel<<<dim3(s->chunk_count, record_count), 256, 0, s->ctx->stream>>>(
 		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, skip_index,
-		static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev));
+		static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),
+		static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag, uint64_t(timeout_ms) * 1000000ull,
+		static_cast<uint32_t*>(status_dev), sig);
+	ZN_CUDA(cudaGetLastError());
+	return ZN_OK;
+}
+
+int zn_scene_expand_visible(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
+                            const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev) {
+	return expand_visible(s, "zn_scene_expand_visible", records_dev, record_count, record_stride_words, skip_index, index_bases, lists_dev,
+	                      list_stride, counts_dev, nullptr, 0, 1, 0, 0, nullptr);
+}
+
+int zn_scene_expand_visible_signalled(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
+                                      const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
+                                      const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
+                                      uint32_t timeout_ms, void* status_dev) {
+	ZN_REQUIRE(flags_dev && status_dev, "zn_scene_expand_visible_signalled: flags_dev / status_dev is NULL");
+	ZN_REQUIRE(records_per_flag >= 1 && timeout_ms >= 1, "zn_scene_expand_visible_signalled: records_per_flag and timeout_ms must be >= 1");
+	return expand_visible(s, "zn_scene_expand_visible_signalled", records_dev, record_count, record_stride_words, skip_index, index_bases,
+	                      lists_dev, list_stride, counts_dev, flags_dev, flag_stride_words, records_per_flag, expected, timeout_ms, status_dev);
+}
+
+int zn_scene_wait_flags(zn_scene* s, const void* flags_dev, uint32_t flag_stride_words, uint32_t flag_count, uint32_t expected,
+                        uint32_t timeout_ms, void* status_dev) {
+	ZN_REQUIRE(s && flags_dev && status_dev, "zn_scene_wait_flags: NULL argument");
+	ZN_REQUIRE(flag_count >= 1 && flag_count <= 64 && timeout_ms >= 1, "zn_scene_wait_flags: flag_count must be in [1, 64], timeout_ms >= 1");
+	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	SignalTargets sig = {};
+	for (uint32_t* flag : s->peer_flags) sig.flag[sig.n++] = flag;
+	sig.value = s->signal_value;
+	wait_flags_kernel<<<1, 64, 0, s->ctx->stream>>>(static_cast<const uint32_t*>(flags_dev), flag_stride_words, flag_count, expected,
+	                                                uint64_t(timeout_ms) * 1000000ull, static_cast<uint32_t*>(status_dev), sig);
 	ZN_CUDA(cudaGetLastError());
 	return ZN_OK;
 }
@@ -320,6 +377,17 @@ int zn_scene_update(zn_scene* s) {
 	rec.n = 1;
 	for (uint32_t* peer : s->peer_records) rec.ptr[rec.n++] = peer;
 	const uint32_t header_words = record_header_words(s->chunk_count);
+	// Peers get the masks of the leading run of small levels from the emit kernel, of every other
+	// level from its level kernel (see emit_chunk).
+	RecordTargets rec_local = rec;
+	rec_local.n = 1;
+	size_t small_levels = 0;
+	uint32_t remote_tiles_below = 0;
+	if (rec.n > 1)
+		while (small_levels < s->levels.size() && s->levels[small_levels].tiles < kSmallLevelTiles) {
+			remote_tiles_below = s->levels[small_levels].tile_base + s->levels[small_levels].tiles;
+			++small_levels;
+		}
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
 	uint32_t* totals_next = s->chunk_total + size_t(s->frame_parity ^ 1u) * s->chunk_count;
 	s->frame_parity ^= 1u;
@@ -345,11 +413,11 @@ int zn_scene_update(zn_scene* s) {
 		if (l == 0)
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<false>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           rec, header_words, totals, ticket, lv.ticket_base));
+			                           l < small_levels ? rec_local : rec, header_words, totals, ticket, lv.ticket_base));
 		else
 			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<true>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
 			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           rec, header_words, totals, ticket, lv.ticket_base));
+			                           l < small_levels ? rec_local : rec, header_words, totals, ticket, lv.ticket_base));
 		// every tile takes one ticket and every CTA one more (the draw that tells it to stop)
 		lv.ticket_base += lv.tiles + grid;
 	}
@@ -359,7 +427,8 @@ int zn_scene_update(zn_scene* s) {
 	cfg.dynamicSmemBytes = 0;
 	cfg.numAttrs = prof ? 0 : 1;
 	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, rec, (const uint32_t*)s->tile_first_entity,
-	                           s->tile_count, s->chunk_count, (const uint32_t*)totals, totals_next, s->index_base, s->visible, s->visible_count));
+	                           s->tile_count, s->chunk_count, (const uint32_t*)totals, totals_next, s->index_base, s->visible, s->visible_count,
+	                           remote_tiles_below));
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
 	return ZN_OK;
 }

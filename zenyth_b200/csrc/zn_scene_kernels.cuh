@@ -23,9 +23,9 @@
 // Data layout in HBM (DESIGN.md "Layout"): inputs are tile-major blocks — for every 256-entity
 // tile one contiguous 16 KiB record of 16 rows x 256 lanes (tx,ty,tz, pitch,yaw,roll, sx,sy,sz,
 // aabb centre xyz, aabb half xyz as float, parent as u32).  Tiles never straddle a hierarchy
-#pragma once
 // level.  Outputs are AoS float[E][16] (what mat4::data() consumers expect,
 // Core/include/math/matrix.hpp:60-61), clipped at the level end by a per-level tensor map.
+#pragma once
 #include "zn_internal.hpp"
 #include "zn_math.cuh"
 #include "zn_ptx.cuh"
@@ -49,6 +49,7 @@ constexpr uint32_t kOutBytes = 2 * kTile * 64;             // world tile + mvp t
 constexpr uint32_t kLevelSmem = kOutBytes + kInBytes + kParBytes + 1024;
 constexpr uint32_t kGather = 0xFFFFFFFFu;                  // tile_prange.y: parents too scattered to stage
 constexpr int kChunkTiles = 32;                            // tiles per emit CTA (8192 entities)
+constexpr uint32_t kSmallLevelTiles = 4096;                // levels below 1Mi entities leave their peer stores to the emit kernel
 
 // Where a frame's visibility record is written: ptr[0] is this rank's own copy; ptr[1..n) are the
 // copies kept by peer GPUs (device pointers into their memory, mapped over NVLink through CUDA
@@ -59,6 +60,33 @@ struct RecordTargets {
 	uint32_t* ptr[kMaxRecordTargets];
 	int n;
 };
+
+// The completion signal of that fused all-gather, also without a collective: `value` — a frame
+// sequence number, monotonically increasing — stored into one flag word in every rank's memory.
+// It is raised by the first CTA of the kernel that FOLLOWS the update on the stream (the expansion
+// of the previous frame): the kernel boundary has completed every store of the level and emit
+// kernels, so one system-scope fence and one release store per peer are all a frame pays.  (Raising
+// it from the emit kernel itself — every CTA fences, the last one to finish signals — was measured
+// 13 us per frame slower: 2048 system-scope fences behind the scatter stores.)
+struct SignalTargets {
+	uint32_t* flag[kMaxRecordTargets];
+	int n;
+	uint32_t value;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+	uint32_t v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+	uint64_t t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
 
 template <bool HAS_PARENT>
 __global__ void __launch_bounds__(kTile, 4)
@@ -255,7 +283,8 @@ __device__ __forceinline__ void scatter_warp_words(const uint4* __restrict__ w4,
 __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ totals, const uint32_t* __restrict__ masks,
                                                const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t chunks,
                                                uint32_t chunk, uint32_t index_base, uint32_t* __restrict__ visible,
-                                               uint32_t* __restrict__ visible_count, const RecordTargets& record_out) {
+                                               uint32_t* __restrict__ visible_count, const RecordTargets& record_out,
+                                               uint32_t remote_tiles_below) {
 	__shared__ uint32_t s_part[8];
 	__shared__ uint32_t s_warp_excl[8];
 	__shared__ uint32_t s_base, s_total;
@@ -269,6 +298,11 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 	// thread t owns mask word t of the chunk: tile chunk*32 + t/8, word t%8
 	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
 	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (t & 7)) : 0u;
+	// Masks of the SMALL leading levels reach the peers from here (coalesced, one kernel boundary)
+	// instead of from their level kernels, whose few microseconds would each end on an NVLink round
+	// trip; the big levels push their own masks tile by tile while they run.
+	if (tile < remote_tiles_below)
+		for (int q = 1; q < record_out.n; ++q) record_out.ptr[q][record_header_words(chunks) + size_t(tile) * kWarpsPerTile + (t & 7)] = word;
 	const uint32_t cnt = __popc(word);
 	uint32_t incl = cnt;
 #pragma unroll
@@ -332,12 +366,33 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 __global__ void __launch_bounds__(256)
 emit_visible_kernel(const __grid_constant__ RecordTargets rec, const uint32_t* __restrict__ tile_first_entity,
                     uint32_t tiles, uint32_t chunks, const uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ chunk_total_next,
-                    uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
+                    uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count, uint32_t remote_tiles_below) {
 	const uint32_t chunk = blockIdx.x;
 	grid_dep_wait();   // masks and totals of every level are complete and visible
 	// rec.ptr[0] is this rank's own record (the masks are read from it); the header goes to all targets
-	emit_chunk(chunk_total, rec.ptr[0] + record_header_words(chunks), tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count, rec);
+	emit_chunk(chunk_total, rec.ptr[0] + record_header_words(chunks), tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count, rec,
+	           remote_tiles_below);
 	if (threadIdx.x == 0) chunk_total_next[chunk] = 0u;
+}
+
+// Signal + wait as a kernel of their own (one thread per flag), for comparison with the form fused
+// into expand_visible_kernel: the kernel boundary orders the expansion after it.
+__global__ void wait_flags_kernel(const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t count, uint32_t expected,
+                                  uint64_t timeout_ns, uint32_t* __restrict__ status, const __grid_constant__ SignalTargets sig) {
+	const uint32_t r = threadIdx.x;
+	if (r == 0 && sig.n > 0) {
+		__threadfence_system();
+		for (int q = 0; q < sig.n; ++q) st_release_sys(sig.flag[q], sig.value);
+	}
+	if (r >= count) return;
+	const uint64_t t0 = global_timer_ns();
+	while (int32_t(ld_acquire_sys(flags + size_t(r) * flag_stride) - expected) < 0) {
+		if (global_timer_ns() - t0 > timeout_ns) {
+			atomicExch(status, 1u + r);
+			break;
+		}
+		__nanosleep(200);
+	}
 }
 
 // Expands `gridDim.y` visibility records (this rank's and its peers', as all-gathered) into their
@@ -352,13 +407,38 @@ struct ExpandBases {
 __global__ void __launch_bounds__(256)
 expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
                       uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, int skip,
-                      uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ counts) {
+                      uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ counts,
+                      const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t expected, uint32_t records_per_flag,
+                      uint64_t timeout_ns, uint32_t* __restrict__ status, const __grid_constant__ SignalTargets sig) {
 	__shared__ __align__(16) uint32_t s_word[256];
 	__shared__ __align__(16) uint32_t s_off[256];
 	__shared__ uint32_t s_first[kChunkTiles];
 	const uint32_t r = blockIdx.y;
+	if (sig.n > 0 && blockIdx.x == 0 && r == 0 && threadIdx.x == 0) {
+		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank
+		__threadfence_system();
+		for (int q = 0; q < sig.n; ++q) st_release_sys(sig.flag[q], sig.value);
+	}
 	if (int(r) == skip) return;
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	if (flags) {
+		// Record r was stored into this GPU's memory by its owner's kernels (SignalTargets above): wait
+		// for the owner's flag to reach this frame's sequence number.  Sequence numbers wrap, hence the
+		// signed distance.  The wait is bounded: a peer that never signals sets *status instead of
+		// hanging the GPU.
+		if (t == 0) {
+			const uint32_t* f = flags + size_t(r / records_per_flag) * flag_stride;
+			const uint64_t t0 = global_timer_ns();
+			while (int32_t(ld_acquire_sys(f) - expected) < 0) {
+				if (global_timer_ns() - t0 > timeout_ns) {
+					atomicExch(status, 1u + r);
+					break;
+				}
+				__nanosleep(200);
+			}
+		}
+		__syncthreads();
+	}
 	const uint32_t* rec = records + size_t(r) * record_stride;
 	const uint32_t* masks = rec + record_header_words(chunks);
 	uint32_t* visible = lists + size_t(r) * list_stride;

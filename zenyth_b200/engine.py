@@ -255,6 +255,30 @@ class Scene:
         check(self._lib.zn_scene_expand_visible(self._h, C.c_void_p(records_ptr), record_count, record_stride_words, skip_index,
                                                 _p(bases), C.c_void_p(lists_ptr), list_stride, C.c_void_p(counts_ptr)))
 
+    def BindPeerSignal(self, flag_ptrs) -> None:
+        """Every update ends by raising these flag words (one per rank, mapped peer memory) to the signal value."""
+        flag_ptrs = list(flag_ptrs)
+        arr = (C.c_void_p * max(len(flag_ptrs), 1))(*flag_ptrs)
+        check(self._lib.zn_scene_bind_peer_signal(self._h, arr, len(flag_ptrs)))
+
+    def WaitFlags(self, flags_ptr: int, flag_stride_words: int, flag_count: int, expected: int, status_ptr: int, timeout_ms: int = 2000) -> None:
+        """A one-CTA kernel on the context stream that waits until every flag has reached `expected` (bounded)."""
+        check(self._lib.zn_scene_wait_flags(self._h, C.c_void_p(flags_ptr), flag_stride_words, flag_count, expected & 0xFFFFFFFF,
+                                            timeout_ms, C.c_void_p(status_ptr)))
+
+    def SetSignalValue(self, value: int) -> None:
+        check(self._lib.zn_scene_set_signal_value(self._h, value & 0xFFFFFFFF))
+
+    def ExpandVisibleSignalled(self, records_ptr: int, record_count: int, record_stride_words: int, lists_ptr: int, list_stride: int,
+                               counts_ptr: int, flags_ptr: int, flag_stride_words: int, expected: int, status_ptr: int,
+                               index_bases=None, skip_index: int = -1, records_per_flag: int = 1, timeout_ms: int = 2000) -> None:
+        """ExpandVisible whose CTAs first wait for the owners' flags (zn_scene_expand_visible_signalled)."""
+        bases = None if index_bases is None else np.ascontiguousarray(index_bases, np.uint32)
+        check(self._lib.zn_scene_expand_visible_signalled(
+            self._h, C.c_void_p(records_ptr), record_count, record_stride_words, skip_index, _p(bases), C.c_void_p(lists_ptr),
+            list_stride, C.c_void_p(counts_ptr), C.c_void_p(flags_ptr), flag_stride_words, records_per_flag, expected & 0xFFFFFFFF,
+            timeout_ms, C.c_void_p(status_ptr)))
+
     def SetIndexBase(self, base: int) -> None:
         check(self._lib.zn_scene_set_index_base(self._h, base))
 

@@ -1,84 +1,156 @@
-"""The exchange fused into the compute kernels over NVLink peer memory.
+"""The exchange fused into the compute kernels over NVLink peer memory — no collective on the data path.
 
-Every rank owns a gathered-records buffer [slots][world][record_words] in plain device memory,
-exports its CUDA IPC handle and maps every peer's buffer (zn_ipc_export / zn_ipc_open).  A scene
-bound to it (zn_scene_bind_visibility_record + zn_scene_bind_peer_records) stores each tile's
-visibility mask — and, from the emit kernel, the record header — straight into slot [rank] of every
-peer's buffer while the level kernels run: plain `st.global` on mapped peer pointers, tile by tile.
-No collective moves the records; a 4-byte all-reduce is the cross-rank barrier that tells a rank
-all peers' frame-k kernels (and therefore their stores into its memory) have completed.  Expansion
-into the ordered index lists is the same `zn_scene_expand_visible` as in RecordExchange.
+Every rank owns ONE plain device allocation
 
-Pipelined like RecordExchange: per frame k a rank runs  update(k) -> barrier(k) [asynchronous] ->
-wait barrier(k-1), expand(k-1).  Update(k+1) on rank r stores into slot (k+1) % slots of every
-peer p.  It is ordered after barrier(k-1) (r waited for it in step k), and barrier(k-1) completes
-only after p finished update(k-1), hence after p's expand(k-3).  So the youngest frame a peer is
-guaranteed to be done expanding is k-3, and a slot may be reused after FOUR frames: slots = 4.
+    records [slots][world][record_words]   gathered visibility records, slot = frame % slots
+    flags   [world] (128-byte stride)      flags[r] = sequence number of the last frame rank r completed
+
+exports its CUDA IPC handle and maps every peer's allocation (zn_ipc_export / zn_ipc_open).  A scene
+bound to it stores each tile's visibility mask — and, from the emit kernel, the record header —
+straight into slot [rank] of every peer's `records` while its kernels run: plain `st.global` on
+mapped peer pointers, tile by tile (zn_scene_bind_visibility_record + zn_scene_bind_peer_records).
+
+Completion travels the same way (signal="flags", the default): the last CTA of the emit kernel,
+after a system-scope fence, raises flags[rank] in every rank's allocation to the frame's sequence
+number (zn_scene_bind_peer_signal), and the expansion kernel of a frame waits on the owners' flags
+itself (zn_scene_expand_visible_signalled, bounded wait).  No NCCL call, no host synchronisation and
+no extra launch per frame.  signal="nccl" keeps the earlier form — a 4-byte all-reduce per frame as
+the cross-rank barrier — for comparison.
+
+A rank's OWN list is not expanded a second time: the scene's emit kernel writes it directly into
+lists[frame % 2][rank] (zn_scene_bind_visible_output) and the expansion skips that record.
+
+Pipeline per frame k:  bind(k); scene.Update(); expand(k-1).
+Slot reuse.  Update(k+1) on rank r stores into slot (k+1) % slots of every peer p.  It is
+stream-ordered after r's expand(k-1), which waited for p's frame k-1 signal; p raised it at the end
+of its update(k-1), i.e. after its expand(k-3).  So the youngest frame a peer is guaranteed to have
+finished reading is k-3 and a slot may be reused after FOUR frames: slots = 4.
+Lists are double-buffered: lists[k % 2] is complete (all ranks) once expand(k) has run and is
+overwritten by update(k+2), so its consumer belongs on the stream between the two.
 """
 from __future__ import annotations
 
 from typing import List, Optional
 
+FLAG_STRIDE_WORDS = 32          # one 128-byte line per writer
+
 
 class PeerRecordExchange:
-    def __init__(self, ctx, record_words: int, capacity: int, world_size: int, rank: int, device, dtype, slots: int = 4, group=None):
+    def __init__(self, ctx, record_words: int, capacity: int, world_size: int, rank: int, device, dtype, slots: int = 4,
+                 signal: str = "flags", timeout_ms: int = 2000, group=None, fused_wait: bool = True):
         import torch
         import torch.distributed as dist
+        if signal not in ("flags", "nccl"):
+            raise ValueError(f"signal must be 'flags' or 'nccl', not {signal!r}")
+        if slots < 4:
+            raise ValueError("slots must be >= 4 (see the module docstring)")
         self.ctx, self.world_size, self.rank, self.slots, self.group = ctx, world_size, rank, slots, group
+        self.signal, self.timeout_ms, self.fused_wait = signal, int(timeout_ms), bool(fused_wait)
         self.record_words, self.capacity = int(record_words), int(capacity)
         self.slot_bytes = world_size * self.record_words * 4
-        self.base = ctx.DeviceAlloc(slots * self.slot_bytes)
+        self.flags_offset = (slots * self.slot_bytes + 127) // 128 * 128
+        self.base = ctx.DeviceAlloc(self.flags_offset + world_size * FLAG_STRIDE_WORDS * 4)
         handles: List[Optional[bytes]] = [None] * world_size
         dist.all_gather_object(handles, ctx.IpcExport(self.base), group=group)
         self.peer_base = [self.base if r == rank else ctx.IpcOpen(handles[r]) for r in range(world_size)]
-        self.lists = torch.empty(world_size * self.capacity, dtype=dtype, device=device)
-        self.counts = torch.zeros(world_size, dtype=dtype, device=device)
+        self.lists = torch.empty(2 * world_size * self.capacity, dtype=dtype, device=device)
+        self.counts = torch.zeros(2 * world_size, dtype=dtype, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.token = torch.zeros(1, dtype=torch.int32, device=device)
         self.work = [None] * slots
+        self.issued = -1            # last frame bound
+        self.expanded = -1          # last frame expanded
         dist.barrier(group=group)   # every rank has mapped every buffer before anyone writes
 
-    def _offset(self, slot: int) -> int:
+    # ---- addresses -------------------------------------------------------------------------------
+    def _record_offset(self, slot: int) -> int:
         return slot * self.slot_bytes + self.rank * self.record_words * 4
 
-    def own_ptr(self, slot: int) -> int:
-        """Where this rank's record of `slot` lives in its OWN gathered buffer."""
-        return self.base + self._offset(slot)
+    def own_record_ptr(self, frame: int) -> int:
+        """Where this rank's record of `frame` lives in its OWN gathered buffer."""
+        return self.base + self._record_offset(frame % self.slots)
 
-    def peer_ptrs(self, slot: int) -> List[int]:
-        """The same slot [rank] inside every PEER's gathered buffer (mapped pointers)."""
-        return [self.peer_base[r] + self._offset(slot) for r in range(self.world_size) if r != self.rank]
+    def peer_record_ptrs(self, frame: int) -> List[int]:
+        """The same cell inside every PEER's gathered buffer (mapped pointers)."""
+        off = self._record_offset(frame % self.slots)
+        return [self.peer_base[r] + off for r in range(self.world_size) if r != self.rank]
 
-    def bind(self, scene, slot: int) -> None:
-        scene.BindVisibilityRecord(self.own_ptr(slot))
-        scene.BindPeerRecords(self.peer_ptrs(slot))
+    def flag_ptrs(self) -> List[int]:
+        """This rank's flag cell in EVERY rank's allocation (its own included)."""
+        off = self.flags_offset + self.rank * FLAG_STRIDE_WORDS * 4
+        return [self.peer_base[r] + off for r in range(self.world_size)]
 
-    def launch(self, slot: int) -> None:
-        """Cross-rank barrier ordered after this rank's update of `slot` (asynchronous)."""
+    def _list_ptr(self, frame: int, r: int = 0) -> int:
+        return self.lists.data_ptr() + ((frame % 2) * self.world_size + r) * self.capacity * 4
+
+    def _count_ptr(self, frame: int, r: int = 0) -> int:
+        return self.counts.data_ptr() + ((frame % 2) * self.world_size + r) * 4
+
+    # ---- per frame -------------------------------------------------------------------------------
+    def bind(self, scene, frame: int) -> None:
+        """Point the scene's next Update at frame `frame`'s cells (own + peers) and its list slot."""
+        assert frame == self.issued + 1, "frames are bound in order"
+        if frame == 0 and self.signal == "flags":
+            scene.BindPeerSignal(self.flag_ptrs())
+        scene.BindVisibilityRecord(self.own_record_ptr(frame))
+        scene.BindPeerRecords(self.peer_record_ptrs(frame))
+        scene.BindVisibleOutput(self._list_ptr(frame, self.rank), self.capacity, self._count_ptr(frame, self.rank))
+        if self.signal == "flags":
+            scene.SetSignalValue(frame + 1)
+        self.issued = frame
+
+    def launch(self, frame: int) -> None:
+        """signal="nccl" only: the cross-rank barrier ordered after this rank's update of `frame`."""
+        if self.signal != "nccl":
+            return
         import torch.distributed as dist
+        slot = frame % self.slots
         assert self.work[slot] is None
         self.work[slot] = dist.all_reduce(self.token, group=self.group, async_op=True)
 
-    def ready(self, slot: int) -> bool:
-        if self.work[slot] is None:
+    def expand(self, scene, frame: int, index_bases=None) -> bool:
+        """Derive every PEER's list of `frame` into lists[frame % 2] (asynchronous); False if the frame
+        was never issued or is already expanded."""
+        if frame < 0 or frame > self.issued or frame <= self.expanded:
             return False
-        self.work[slot].wait()      # the current stream waits for the barrier
-        self.work[slot] = None
+        assert frame == self.expanded + 1, "frames are expanded in order"
+        records = self.base + (frame % self.slots) * self.slot_bytes
+        if self.signal == "flags" and not self.fused_wait:
+            scene.WaitFlags(self.base + self.flags_offset, FLAG_STRIDE_WORDS, self.world_size, frame + 1, self.status.data_ptr(),
+                            timeout_ms=self.timeout_ms)
+            scene.ExpandVisible(records, self.world_size, self.record_words, self._list_ptr(frame), self.capacity,
+                                self._count_ptr(frame), index_bases=index_bases, skip_index=self.rank)
+        elif self.signal == "flags":
+            scene.ExpandVisibleSignalled(records, self.world_size, self.record_words, self._list_ptr(frame), self.capacity,
+                                         self._count_ptr(frame), self.base + self.flags_offset, FLAG_STRIDE_WORDS, frame + 1,
+                                         self.status.data_ptr(), index_bases=index_bases, skip_index=self.rank,
+                                         timeout_ms=self.timeout_ms)
+        else:
+            slot = frame % self.slots
+            self.work[slot].wait()      # the current stream waits for the barrier
+            self.work[slot] = None
+            scene.ExpandVisible(records, self.world_size, self.record_words, self._list_ptr(frame), self.capacity,
+                                self._count_ptr(frame), index_bases=index_bases, skip_index=self.rank)
+        self.expanded = frame
         return True
 
-    def expand(self, scene, slot: int, index_bases=None) -> None:
-        scene.ExpandVisible(self.base + slot * self.slot_bytes, self.world_size, self.record_words, self.lists.data_ptr(), self.capacity,
-                            self.counts.data_ptr(), index_bases=index_bases)
-
     def result(self):
-        counts = [int(c) for c in self.counts.tolist()]
-        return counts, self.lists.view(self.world_size, self.capacity)
+        """(counts, lists[world, capacity]) of the last expanded frame (synchronises)."""
+        status = int(self.status.item())
+        if status:
+            raise RuntimeError(f"rank {self.rank}: rank {status - 1} never signalled a frame within {self.timeout_ms} ms")
+        f = self.expanded % 2
+        counts = [int(c) for c in self.counts[f * self.world_size: (f + 1) * self.world_size].tolist()]
+        return counts, self.lists.view(2, self.world_size, self.capacity)[f]
 
     def close(self, scene=None) -> None:
         import torch
         import torch.distributed as dist
         if scene is not None:
             scene.BindPeerRecords([])
+            scene.BindPeerSignal([])
             scene.BindVisibilityRecord(None)
+            scene.BindVisibleOutput(None)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)          # nobody still writes into a buffer that is about to go away
         for r, p in enumerate(self.peer_base):
