@@ -303,9 +303,23 @@ def run_ours(args) -> None:
     launches_per_update = scene.LaunchesPerUpdate()
 
     frame_no = [0]
-    use_lists = distributed and args.exchange == "lists"
-    use_records = distributed and args.exchange == "records"
-    use_peer = distributed and args.exchange in ("peer", "peer-nccl", "peer-waitkernel")
+    mode = args.exchange if distributed else "none"
+    fallback_note = ""
+    index_bases = np.asarray([(r * E) % 2 ** 32 for r in range(world_size)], np.uint32)
+    if mode.startswith("peer"):
+        # The visibility records (1 bit per entity), but no collective moves them: the level and emit
+        # kernels store every tile's mask and the record header straight into all peers' buffers over
+        # NVLink (CUDA IPC mapped peer memory); completion flags travel the same way and the
+        # expansion kernel waits on them itself ("peer-nccl": a 4-byte all-reduce per frame is the
+        # cross-rank barrier instead; "peer-waitkernel": signal + wait as a launch of their own).
+        from zenyth_b200.peer_exchange import PeerRecordExchange
+        try:
+            exchange = PeerRecordExchange(ctx, bufs.visibility_record_words, E, world_size, rank, dev, torch.int32, slots=4,
+                                          signal="nccl" if mode == "peer-nccl" else "flags", fused_wait=mode != "peer-waitkernel")
+        except RuntimeError as e:    # raised on every rank together: peer mapping is not possible on this box
+            fallback_note = f"--exchange {mode} unavailable ({e}); ran --exchange records"
+            mode = "records"
+    use_lists, use_records, use_peer = mode == "lists", mode == "records", mode.startswith("peer")
     if use_lists:
         # The exchange of the path as SURVEY §8e words it: all-gather the visible counts, then the
         # compacted index lists.  Double-buffered: the scene writes frame k's list straight into
@@ -318,18 +332,6 @@ def run_ours(args) -> None:
         # every rank expands all of them into the ordered lists (zenyth_b200.distributed.RecordExchange).
         from zenyth_b200.distributed import RecordExchange
         exchange = RecordExchange(bufs.visibility_record_words, E, world_size, dev, torch.int32, slots=2)
-        index_bases = np.asarray([(r * E) % 2 ** 32 for r in range(world_size)], np.uint32)
-    if use_peer:
-        # The same records, but no collective moves them: the level and emit kernels store every
-        # tile's mask and the record header straight into all peers' buffers over NVLink (CUDA IPC
-        # mapped peer memory); the emit kernel's last CTA raises a flag at every peer and the
-        # expansion kernel waits on those flags itself ("peer-nccl": a 4-byte all-reduce per frame
-        # is the cross-rank barrier instead).
-        from zenyth_b200.peer_exchange import PeerRecordExchange
-        exchange = PeerRecordExchange(ctx, bufs.visibility_record_words, E, world_size, rank, dev, torch.int32, slots=4,
-                                      signal="nccl" if args.exchange == "peer-nccl" else "flags",
-                                      fused_wait=args.exchange != "peer-waitkernel")
-        index_bases = np.asarray([(r * E) % 2 ** 32 for r in range(world_size)], np.uint32)
 
     def step():
         slot = frame_no[0] % 2
@@ -510,6 +512,7 @@ def run_ours(args) -> None:
                        "visible_fraction": visible / E,
                        "l2": "inputs 1.07 GB + outputs 2.15 GB per step >> 126 MB L2, no flush needed" if E > 4_000_000
                              else "footprint ~%d MB vs 126 MB L2" % (E * 192 // 1_000_000),
+                       "exchange": mode,
                        "collective": (
                            ("NCCL all_gather of visible counts + index lists every step, double-buffered: the exchange of "
                             "frame k overlaps the update of frame k+1; the timed region ends after the last exchange; "
@@ -522,10 +525,10 @@ def run_ours(args) -> None:
                             "the visibility record tile by tile into every peer's buffer (CUDA IPC mapped pointers); "
                             + ("the emit kernel's last CTA raises a sequence flag at every peer (fence.sys + st.release.sys) and the "
                                "expansion kernel waits on the owners' flags itself — no NCCL call in the timed region; "
-                               if args.exchange != "peer-nccl" else "a 4-byte NCCL all-reduce per frame is the cross-rank barrier; ")
+                               if mode != "peer-nccl" else "a 4-byte NCCL all-reduce per frame is the cross-rank barrier; ")
                             + "every rank expands its peers' records into the ordered index lists + counts (its own list comes "
                               "straight from its emit kernel)") if use_peer
-                           else "none (1 GPU)")},
+                           else "none (1 GPU)") + ((" [" + fallback_note + "]") if fallback_note else "")},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -729,10 +732,11 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["mesh64m", "scenes8x32m"], default="h8geo16m")
-    ap.add_argument("--exchange", choices=["records", "lists", "peer", "peer-nccl", "peer-waitkernel"], default="records",
-                    help="N>1: all-gather visibility records and expand locally (records); all-gather the index lists (lists); or let "
-                         "the kernels store the records straight into peer GPUs' memory over NVLink and signal completion with "
-                         "flags in peer memory (peer) or a 4-byte all-reduce (peer-nccl)")
+    ap.add_argument("--exchange", choices=["peer", "records", "lists", "peer-nccl", "peer-waitkernel"], default="peer",
+                    help="N>1: the kernels store the visibility records straight into peer GPUs' memory over NVLink and signal "
+                         "completion with flags in peer memory (peer, default; falls back to records where peer mapping is refused); "
+                         "NCCL all-gather of the records (records) or of the index lists (lists); peer stores with a 4-byte "
+                         "all-reduce as the barrier (peer-nccl) or with signal + wait as a kernel of their own (peer-waitkernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     args = ap.parse_args()

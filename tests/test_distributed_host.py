@@ -109,3 +109,114 @@ def test_visible_gather_world_size_2_gloo(tmp_path):
     mp.spawn(_worker, args=(2, port, 50_000, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert (tmp_path / f"rank{r}.ok").read_text() == "1"
+
+
+# ---- PeerRecordExchange: the host protocol of the collective-free exchange, on fakes ----------------
+class _FakeCtx:
+    """Stands in for GpuContext: 'device memory' is a Python dict keyed by fake addresses shared
+    through nothing at all — only the address arithmetic and the call protocol are under test."""
+
+    def __init__(self, rank, fail_export=False, fail_open=False):
+        self.rank, self.fail_export, self.fail_open = rank, fail_export, fail_open
+        self.opened, self.closed, self.freed = [], [], []
+
+    def DeviceAlloc(self, nbytes):
+        self.nbytes = nbytes
+        return 0x1000_0000 * (self.rank + 1)
+
+    def DeviceFree(self, ptr):
+        self.freed.append(ptr)
+
+    def IpcExport(self, ptr):
+        if self.fail_export:
+            raise RuntimeError("export refused")
+        return ptr.to_bytes(8, "little") + bytes(56)
+
+    def IpcOpen(self, handle):
+        if self.fail_open:
+            raise RuntimeError("open refused")
+        ptr = int.from_bytes(handle[:8], "little") + 0x8_0000_0000      # a peer maps at another address
+        self.opened.append(ptr)
+        return ptr
+
+    def IpcClose(self, ptr):
+        self.closed.append(ptr)
+
+
+class _FakeScene:
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def record(*a, **k):
+            self.calls.append((name, a, k))
+        return record
+
+
+def _peer_worker(rank: int, world: int, port: int, out_dir: str):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from zenyth_b200.peer_exchange import FLAG_STRIDE_WORDS, PeerRecordExchange
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    words, cap = 1000, 5000
+    # (1) a rank that cannot export / map: EVERY rank raises, nobody hangs, nothing leaks
+    for kw in ({"fail_export": rank == 1}, {"fail_open": rank == 0}):
+        ctx = _FakeCtx(rank, **kw)
+        try:
+            PeerRecordExchange(ctx, words, cap, world, rank, "cpu", torch.int32)
+            ok = False
+        except RuntimeError as e:
+            ok &= "peer memory unavailable" in str(e)
+        ok &= sorted(ctx.closed) == sorted(ctx.opened) and len(ctx.freed) <= 1
+    # (2) the protocol
+    ctx, sc = _FakeCtx(rank), _FakeScene()
+    ex = PeerRecordExchange(ctx, words, cap, world, rank, "cpu", torch.int32)
+    own, peer = 0x1000_0000 * (rank + 1), 0x1000_0000 * (2 - rank) + 0x8_0000_0000
+    slot_bytes = world * words * 4
+    flags_off = (4 * slot_bytes + 127) // 128 * 128
+    ok &= ctx.nbytes == flags_off + world * FLAG_STRIDE_WORDS * 4
+    ok &= ex.flag_ptrs() == [(own if r == rank else peer) + flags_off + rank * 128 for r in range(world)]
+    for k in range(6):
+        ex.bind(sc, k)
+        sc.Update()
+        ex.launch(k)
+        ok &= ex.expand(sc, k - 1) == (k >= 1)
+    ok &= not ex.expand(sc, 4)                       # already expanded
+    ok &= ex.expand(sc, 5) and not ex.expand(sc, 6)   # never issued
+    names = [c[0] for c in sc.calls]
+    ok &= names[:6] == ["BindPeerSignal", "BindVisibilityRecord", "BindPeerRecords", "BindVisibleOutput", "SetSignalValue", "Update"]
+    ok &= names.count("BindPeerSignal") == 1 and names.count("ExpandVisibleSignalled") == 6
+    binds = [c for c in sc.calls if c[0] == "BindVisibilityRecord"]
+    peers = [c for c in sc.calls if c[0] == "BindPeerRecords"]
+    for k in range(6):
+        off = (k % 4) * slot_bytes + rank * words * 4
+        ok &= binds[k][1] == (own + off,) and peers[k][1] == ([peer + off],)
+    expands = [c for c in sc.calls if c[0] == "ExpandVisibleSignalled"]
+    for k, c in enumerate(expands):                 # frame k: slot k%4, list half k%2, waits for sequence k+1, skips itself
+        a, kw = c[1], c[2]
+        ok &= a[0] == own + (k % 4) * slot_bytes and a[1:3] == (world, words)
+        ok &= a[3] == ex.lists.data_ptr() + (k % 2) * world * cap * 4 and a[6] == own + flags_off and a[8] == k + 1
+        ok &= kw["skip_index"] == rank
+    signal_values = [c[1][0] for c in sc.calls if c[0] == "SetSignalValue"]
+    ok &= signal_values == [1, 2, 3, 4, 5, 6]
+    ex.close(sc)
+    ok &= ctx.closed == [peer] and ctx.freed == [own]
+    with open(os.path.join(out_dir, f"peer{rank}.ok"), "w") as f:
+        f.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_peer_record_exchange_protocol_world_size_2_gloo(tmp_path, monkeypatch):
+    import torch
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert (tmp_path / f"peer{r}.ok").read_text() == "1"

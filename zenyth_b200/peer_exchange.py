@@ -46,13 +46,32 @@ class PeerRecordExchange:
             raise ValueError("slots must be >= 4 (see the module docstring)")
         self.ctx, self.world_size, self.rank, self.slots, self.group = ctx, world_size, rank, slots, group
         self.signal, self.timeout_ms, self.fused_wait = signal, int(timeout_ms), bool(fused_wait)
+        self.device = torch.device(device)
         self.record_words, self.capacity = int(record_words), int(capacity)
         self.slot_bytes = world_size * self.record_words * 4
         self.flags_offset = (slots * self.slot_bytes + 127) // 128 * 128
-        self.base = ctx.DeviceAlloc(self.flags_offset + world_size * FLAG_STRIDE_WORDS * 4)
+        # Set-up is collective; a rank that cannot allocate, export or map still takes part in every
+        # rendezvous below, so all ranks learn of the failure together (and raise together) instead of
+        # one of them hanging the others in a barrier.
+        self.base, self.peer_base, problem = 0, [], ""
+        try:
+            self.base = ctx.DeviceAlloc(self.flags_offset + world_size * FLAG_STRIDE_WORDS * 4)
+            handle = ctx.IpcExport(self.base)
+        except Exception as e:      # noqa: BLE001 - reported to every rank below
+            handle, problem = None, f"rank {rank}: {e}"
         handles: List[Optional[bytes]] = [None] * world_size
-        dist.all_gather_object(handles, ctx.IpcExport(self.base), group=group)
-        self.peer_base = [self.base if r == rank else ctx.IpcOpen(handles[r]) for r in range(world_size)]
+        dist.all_gather_object(handles, handle, group=group)
+        if not problem and all(h is not None for h in handles):
+            try:
+                for r in range(world_size):
+                    self.peer_base.append(self.base if r == rank else ctx.IpcOpen(handles[r]))
+            except Exception as e:  # noqa: BLE001
+                problem = f"rank {rank}: {e}"
+        problems: List[Optional[str]] = [None] * world_size
+        dist.all_gather_object(problems, problem, group=group)
+        if any(problems) or any(h is None for h in handles):
+            self._release()
+            raise RuntimeError("peer memory unavailable: " + "; ".join(p for p in problems if p))
         self.lists = torch.empty(2 * world_size * self.capacity, dtype=dtype, device=device)
         self.counts = torch.zeros(2 * world_size, dtype=dtype, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
@@ -151,10 +170,17 @@ class PeerRecordExchange:
             scene.BindPeerSignal([])
             scene.BindVisibilityRecord(None)
             scene.BindVisibleOutput(None)
-        torch.cuda.synchronize()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)          # nobody still writes into a buffer that is about to go away
+        self._release()
+        dist.barrier(group=self.group)
+
+    def _release(self) -> None:
         for r, p in enumerate(self.peer_base):
             if r != self.rank:
                 self.ctx.IpcClose(p)
-        dist.barrier(group=self.group)
-        self.ctx.DeviceFree(self.base)
+        self.peer_base = []
+        if self.base:
+            self.ctx.DeviceFree(self.base)
+            self.base = 0
