@@ -269,6 +269,12 @@ typedef struct zn_mesh_buffers {
 	uint32_t vertex_count;
 } zn_mesh_buffers;
 int zn_mesh_device_buffers(zn_mesh* mesh, zn_mesh_buffers* out);
+/* Mesh-batch ingest, the companion of zn_scene_save/load.  Little-endian: "ZNMESH01", uint32
+ * vertex_count, uint32 instance_count, uint32 instance_first_vertex[instance_count+1], float32
+ * position[V][3], normal[V][3], model[I][16] (the matrices in use at save time: a bound scene's
+ * world matrices are written out as plain models).  zn_mesh_load creates the mesh it reads. */
+int zn_mesh_save(zn_mesh* mesh, const char* path);
+int zn_mesh_load(zn_ctx* ctx, const char* path, zn_mesh** out_mesh);
 
 /* ---- synthetic inputs generated on the device (bench / test support).
  *      A stateless hash of (seed, index, field) -> float, bit-identical to the host generator. */

@@ -80,3 +80,54 @@ def test_models_bound_to_scene_world(oracle, gpu_ctx):
     assert same_values(got_p, ref_p) and same_values(got_n, ref_n)
     m.Close()
     sc.Close()
+
+
+def test_mesh_file_round_trip(oracle, gpu_ctx, tmp_path):
+    """N4: the ZNMESH01 dump — a file written with numpy loads into a batch that matches the oracle,
+    saving it reproduces the file byte for byte, and a batch bound to a scene saves its world matrices."""
+    import zenyth_b200 as zn
+    counts = np.array([3, 1024, 0, 700, 2049], np.uint32)          # ragged, one empty instance
+    first = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+    V, I = int(first[-1]), counts.size
+    pos, nrm = oracle.synth_mesh(BASE_SEED + 21, V)
+    models = models_from_scene(oracle, I)
+    path = tmp_path / "batch.znmesh"
+    with open(path, "wb") as f:
+        f.write(b"ZNMESH01")
+        f.write(np.asarray([V, I], np.uint32).tobytes())
+        f.write(first.tobytes())
+        f.write(pos.astype(np.float32).tobytes())
+        f.write(nrm.astype(np.float32).tobytes())
+        f.write(models.astype(np.float32).reshape(I, 16).tobytes())
+    m = zn.Mesh.LoadFile(gpu_ctx, path)
+    assert (m.vertex_count, m.instance_count) == (V, I)
+    m.Transform()
+    got_p, got_n = m.Read()
+    ref_p, ref_n = oracle.mesh_transform(first, models, pos, nrm)
+    assert same_values(got_p, ref_p) and same_values(got_n, ref_n)
+    out = tmp_path / "again.znmesh"
+    m.SaveFile(out)
+    assert out.read_bytes() == path.read_bytes()
+    # bound to a scene: the scene's world matrices are what gets written
+    arrays = oracle.synth_scene(BASE_SEED + 2, [I], fanout=1)
+    arrays["parent"] = None
+    view, proj = camera(oracle)
+    sc = zn.Scene(gpu_ctx, I)
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    sc.Update()
+    m.BindSceneModels(sc, 0)
+    bound = tmp_path / "bound.znmesh"
+    m.SaveFile(bound)
+    a, b = bound.read_bytes(), path.read_bytes()                # models_from_scene builds the same scene
+    assert a[:-64 * I] == b[:-64 * I]
+    assert np.array_equal(np.frombuffer(a[-64 * I:], np.float32), np.frombuffer(b[-64 * I:], np.float32))   # -0.0 == 0.0
+    m.Close()
+    sc.Close()
+    for name, payload in (("bad.znmesh", b"NOTAMESH" + bytes(64)), ("short.znmesh", path.read_bytes()[:-20])):
+        p = tmp_path / name
+        p.write_bytes(payload)
+        with pytest.raises(zn.ZenythError):
+            zn.Mesh.LoadFile(gpu_ctx, p)
+    with pytest.raises(zn.ZenythError):
+        zn.Mesh.LoadFile(gpu_ctx, tmp_path / "missing.znmesh")

@@ -96,6 +96,8 @@ PROTOTYPES = {
     "zn_scene_build_draw": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp]),
     "zn_scene_save": (C.c_int, [vp, C.c_char_p]),
     "zn_scene_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+    "zn_mesh_save": (C.c_int, [vp, C.c_char_p]),
+    "zn_mesh_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "zn_scene_frame_host": (C.c_int, [vp, C.POINTER(FrameHostIO)]),
     "zn_scene_frame_host_submit": (C.c_int, [vp, C.POINTER(FrameHostIO)]),
     "zn_scene_frame_host_wait": (C.c_int, [vp, C.POINTER(FrameHostIO)]),

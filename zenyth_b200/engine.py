@@ -467,6 +467,24 @@ class Mesh:
         check(self._lib.zn_mesh_read_inputs(self._h, first, count, _p(pos), _p(nrm)))
         return pos, nrm
 
+    def SaveFile(self, path: str) -> None:
+        """Write the batch (ranges, vertices, the model matrices in use) as a ZNMESH01 file (zn_mesh_save)."""
+        check(self._lib.zn_mesh_save(self._h, str(path).encode()))
+
+    @classmethod
+    def LoadFile(cls, ctx: "GpuContext", path: str) -> "Mesh":
+        """Create a mesh batch from a ZNMESH01 file (zn_mesh_load)."""
+        lib = _capi.load()
+        h = C.c_void_p()
+        check(lib.zn_mesh_load(ctx._h, str(path).encode(), C.byref(h)))
+        with open(path, "rb") as f:
+            f.seek(8)
+            v, i = np.frombuffer(f.read(8), np.uint32)
+        self = cls.__new__(cls)
+        self._lib, self.ctx, self._h = lib, ctx, h
+        self.vertex_count, self.instance_count = int(v), int(i)
+        return self
+
     def DeviceBuffers(self) -> _capi.MeshBuffers:
         b = _capi.MeshBuffers()
         check(self._lib.zn_mesh_device_buffers(self._h, C.byref(b)))
