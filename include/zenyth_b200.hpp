@@ -140,6 +140,16 @@ public:
 	Scene& operator=(const Scene&) = delete;
 	Scene(Scene&& o) noexcept : m_scene(std::exchange(o.m_scene, nullptr)), m_entityCount(o.m_entityCount) {}
 
+	// Scene ingest: the ZNSCENE1 dump described in zenyth_b200.h (the reference has no on-disk format).
+	[[nodiscard]] static Scene LoadFile(GpuContext& ctx, const std::string& path) {
+		zn_scene* h = nullptr;
+		detail::Check(zn_scene_load(ctx.Handle(), path.c_str(), &h), "Scene::LoadFile");
+		Scene s(h);
+		s.m_entityCount = s.DeviceBuffers().entity_count;
+		return s;
+	}
+	void SaveFile(const std::string& path) { detail::Check(zn_scene_save(m_scene, path.c_str()), "Scene::SaveFile"); }
+
 	[[nodiscard]] uint32_t EntityCount() const noexcept { return m_entityCount; }
 
 	// Arrays of `count` records `strideBytes` apart: 12 for packed floats, 16 for arrays of
@@ -171,6 +181,25 @@ public:
 
 	// One frame, asynchronous: world matrices over the hierarchy, MVP, visible list.
 	void Update() { detail::Check(zn_scene_update(m_scene), "Scene::Update"); }
+
+	// The all-in-one frame a CPU engine swaps in: uploads the packed host arrays that are not null,
+	// updates, downloads what is asked for; returns the visible count after the data has landed.
+	uint32_t FrameHost(const float* position, const float* rotation, const float* scale, float* world, float* mvp, uint32_t* visible) {
+		zn_frame_host_io io{position, rotation, scale, world, mvp, visible, 0};
+		detail::Check(zn_scene_frame_host(m_scene, &io), "Scene::FrameHost");
+		return io.visible_count;
+	}
+	// The same frame pipelined, up to two in flight: the upload of frame k+1 overlaps the update and
+	// the download of frame k.  The arrays must stay untouched until the matching WaitFrameHost.
+	void SubmitFrameHost(const float* position, const float* rotation, const float* scale) {
+		const zn_frame_host_io io{position, rotation, scale, nullptr, nullptr, nullptr, 0};
+		detail::Check(zn_scene_frame_host_submit(m_scene, &io), "Scene::SubmitFrameHost");
+	}
+	uint32_t WaitFrameHost(uint32_t* visible) {
+		zn_frame_host_io io{nullptr, nullptr, nullptr, nullptr, nullptr, visible, 0};
+		detail::Check(zn_scene_frame_host_wait(m_scene, &io), "Scene::WaitFrameHost");
+		return io.visible_count;
+	}
 
 	[[nodiscard]] uint32_t VisibleCount() {
 		uint32_t n = 0;
@@ -208,6 +237,7 @@ public:
 	[[nodiscard]] zn_scene* Handle() const noexcept { return m_scene; }
 
 private:
+	explicit Scene(zn_scene* adopted) noexcept : m_scene(adopted) {}
 	zn_scene* m_scene = nullptr;
 	uint32_t m_entityCount = 0;
 };
@@ -233,6 +263,16 @@ public:
 	Mesh& operator=(const Mesh&) = delete;
 	Mesh(Mesh&& o) noexcept : m_mesh(std::exchange(o.m_mesh, nullptr)), m_vertexCount(o.m_vertexCount) {}
 
+	// Mesh-batch ingest: the ZNMESH01 dump described in zenyth_b200.h.
+	[[nodiscard]] static Mesh LoadFile(GpuContext& ctx, const std::string& path) {
+		zn_mesh* h = nullptr;
+		detail::Check(zn_mesh_load(ctx.Handle(), path.c_str(), &h), "Mesh::LoadFile");
+		Mesh m(h);
+		m.m_vertexCount = m.DeviceBuffers().vertex_count;
+		return m;
+	}
+	void SaveFile(const std::string& path) { detail::Check(zn_mesh_save(m_mesh, path.c_str()), "Mesh::SaveFile"); }
+
 	void SetVertices(uint32_t first, uint32_t count, const float* position, const float* normal, size_t strideBytes) {
 		detail::Check(zn_mesh_set_vertices(m_mesh, first, count, position, normal, strideBytes), "Mesh::SetVertices");
 	}
@@ -256,6 +296,7 @@ public:
 	[[nodiscard]] uint32_t VertexCount() const noexcept { return m_vertexCount; }
 
 private:
+	explicit Mesh(zn_mesh* adopted) noexcept : m_mesh(adopted) {}
 	zn_mesh* m_mesh = nullptr;
 	uint32_t m_vertexCount = 0;
 };

@@ -93,6 +93,7 @@ def test_cpp_headless_sandbox_runs_the_reference_loop_shape(gpu_ctx):
     assert r.returncode == 0, r.stdout + r.stderr
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["entities"] == 4681 and 0 < out["visible"] <= 4681 and out["ms_per_frame"] > 0
+    assert out["file_round_trip"] is True             # Scene::SaveFile / LoadFile / FrameHost of the C++ layer
 
 
 def test_reference_application_loop_drives_the_gpu_scene(gpu_ctx):

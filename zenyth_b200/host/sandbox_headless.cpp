@@ -7,7 +7,8 @@
 // tree, fan-out 8, one root = 4,681 entities, camera at the Sandbox's 1280x720 viewport — with
 // OnUpdate spinning the root (yaw += dt) and the SceneRenderer seam doing the GPU frame.
 //
-//   sandbox_headless [frames]          run on GPU 0, print ms/frame and the visible count
+//   sandbox_headless [frames]          run on GPU 0, print ms/frame and the visible count, then check that the
+//                                      scene survives SaveFile -> LoadFile -> FrameHost with the same visible list
 //   sandbox_headless --expect-no-gpu   exit 0 iff creating a context throws std::runtime_error
 //
 // Build: g++ -std=c++17 -Iinclude zenyth_b200/host/sandbox_headless.cpp -Lzenyth_b200/lib -lzenyth_b200
@@ -73,6 +74,20 @@ public:
 		return std::chrono::duration<double, std::milli>(t1 - t0).count() / frames;
 	}
 	uint32_t VisibleCount() const { return m_renderer.VisibleCount(); }
+
+	// Scene ingest through the C++ layer: dump the scene, load it into a second Scene and run one
+	// all-in-one host frame on it (no uploads: the file carried the inputs); the visible list must be
+	// the one the live scene just produced.
+	bool FileRoundTrip(const std::string& path) {
+		m_scene.SaveFile(path);
+		Zenyth::Scene copy = Zenyth::Scene::LoadFile(m_ctx, path);
+		if (copy.EntityCount() != m_scene.EntityCount()) return false;
+		copy.SetCamera(m_camera);
+		std::vector<uint32_t> visible(copy.EntityCount());
+		const uint32_t n = copy.FrameHost(nullptr, nullptr, nullptr, nullptr, nullptr, visible.data());
+		visible.resize(n);
+		return visible == m_scene.Visible();
+	}
 	uint32_t EntityCount() const { return m_scene.EntityCount(); }
 
 private:
@@ -113,8 +128,12 @@ int main(int argc, char** argv) {
 		HeadlessSandbox app;
 		app.Run(10);
 		const double ms = app.Run(frames);
-		std::printf("{\"entities\": %u, \"frames\": %d, \"ms_per_frame\": %.4f, \"visible\": %u}\n", app.EntityCount(), frames, ms,
-		            app.VisibleCount());
+		const char* tmp = std::getenv("TMPDIR");
+		const std::string path = std::string(tmp ? tmp : "/tmp") + "/sandbox_headless.znscene";
+		const bool roundTrip = app.FileRoundTrip(path);
+		std::remove(path.c_str());
+		std::printf("{\"entities\": %u, \"frames\": %d, \"ms_per_frame\": %.4f, \"visible\": %u, \"file_round_trip\": %s}\n", app.EntityCount(),
+		            frames, ms, app.VisibleCount(), roundTrip ? "true" : "false");
 	} catch (const std::runtime_error& e) {
 		std::fprintf(stderr, "sandbox_headless: %s\n", e.what());
 		return 2;
