@@ -220,3 +220,76 @@ def test_peer_record_exchange_protocol_world_size_2_gloo(tmp_path, monkeypatch):
     mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert (tmp_path / f"peer{r}.ok").read_text() == "1"
+
+
+# ---- one scene split over ranks by root subtree (entity shards) ------------------------------------
+def _forest(rng, level_sizes, orphan_rate=0.0):
+    """A random level-ordered forest: children sorted by parent, optional extra roots below level 0."""
+    offs = np.concatenate([[0], np.cumsum(level_sizes)]).astype(np.uint32)
+    E = int(offs[-1])
+    parent = np.full(E, 0xFFFFFFFF, np.uint32)
+    for l in range(1, len(level_sizes)):
+        lo, hi = int(offs[l]), int(offs[l + 1])
+        p = np.sort(rng.integers(int(offs[l - 1]), lo, hi - lo)).astype(np.uint32)
+        p[rng.random(hi - lo) < orphan_rate] = 0xFFFFFFFF
+        parent[lo:hi] = p
+    a = {"position": rng.uniform(-10, 10, (E, 3)), "rotation": rng.uniform(-3, 3, (E, 3)), "scale": rng.uniform(0.9, 1.1, (E, 3)),
+         "aabb_center": rng.uniform(-0.2, 0.2, (E, 3)), "aabb_half": rng.uniform(0.1, 1.0, (E, 3))}
+    a = {k: v.astype(np.float32) for k, v in a.items()}
+    a["position"][: level_sizes[0]] *= 100.0
+    a["parent"], a["level_offsets"] = parent, offs
+    return a
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("orphans", [0.0, 0.05])
+def test_scene_sharded_by_root_subtree_equals_the_whole_scene(oracle, world, orphans):
+    from oracle.binding import camera
+    from zenyth_b200.distributed import merge_visible, root_of_entities, shard_scene_by_roots
+    rng = np.random.default_rng(7 + world)
+    scene = _forest(rng, [11, 90, 700, 3000, 1500], orphan_rate=orphans)
+    view, proj = camera(oracle)
+    whole = oracle.scene_update(scene, view, proj)
+    shards = shard_scene_by_roots(scene, world)
+    assert len(shards) == world and all(s.entity_count > 0 for s in shards)
+    every = np.sort(np.concatenate([s.global_index for s in shards]))
+    assert np.array_equal(every, np.arange(scene["parent"].size))            # a partition
+    root = root_of_entities(scene["level_offsets"], scene["parent"])
+    lists = []
+    for s in shards:
+        assert np.all(np.diff(s.global_index.astype(np.int64)) > 0)
+        # hierarchy-closed: every parent is in the same shard, in an earlier level of it
+        p = s.arrays["parent"]
+        has = p != 0xFFFFFFFF
+        assert np.array_equal(s.global_index[p[has]], scene["parent"][s.global_index[has]])
+        offs = s.arrays["level_offsets"].astype(np.int64)
+        level_of = np.searchsorted(offs, np.arange(s.entity_count), side="right") - 1
+        assert np.all(level_of[p[has]] < level_of[has]) and np.all(np.diff(offs) > 0)
+        for l in range(offs.size - 1):                                       # children stay sorted by parent
+            seg = p[offs[l]:offs[l + 1]]
+            seg = seg[seg != 0xFFFFFFFF].astype(np.int64)
+            assert np.all(np.diff(seg) >= 0)
+        assert np.unique(root[s.global_index]).size == np.count_nonzero(~has)
+        got = oracle.scene_update(s.arrays, view, proj)
+        assert np.array_equal(got["world"], whole["world"][s.global_index])  # bit-identical, not merely close
+        assert np.array_equal(got["mvp"], whole["mvp"][s.global_index])
+        lists.append(s.to_global(got["visible"]))
+    assert np.array_equal(merge_visible(lists), whole["visible"])
+    sizes = [s.entity_count for s in shards]
+    assert max(sizes) <= 2.5 * (sum(sizes) / world) + 1
+
+
+def test_scene_sharding_rejects_what_it_cannot_split():
+    from zenyth_b200.distributed import root_of_entities, shard_scene_by_roots
+    a = _forest(np.random.default_rng(1), [2, 10, 30])
+    with pytest.raises(ValueError):
+        shard_scene_by_roots(a, 3)                    # two root subtrees, three ranks
+    with pytest.raises(ValueError):
+        shard_scene_by_roots(a, 0)
+    bad = dict(a, parent=a["parent"].copy())
+    bad["parent"][5] = 20                             # a parent in a LATER level
+    with pytest.raises(ValueError):
+        root_of_entities(bad["level_offsets"], bad["parent"])
+    flat = {k: v for k, v in _forest(np.random.default_rng(2), [100]).items() if k != "parent"}
+    shards = shard_scene_by_roots(flat, 4)            # no parent array: every entity is a root
+    assert [s.entity_count for s in shards] == [25, 25, 25, 25]

@@ -330,3 +330,22 @@ def test_scene_file_round_trip(oracle, gpu_ctx, tmp_path):
         zn.Scene.LoadFile(gpu_ctx, bad)
     with pytest.raises(zn.ZenythError):
         zn.Scene.LoadFile(gpu_ctx, tmp_path / "missing.znscene")
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_one_scene_sharded_by_root_subtree(oracle, gpu_ctx, world):
+    """SURVEY §8e, 'within one scene': hierarchy-closed shards (zenyth_b200.distributed.shard_scene_by_roots),
+    each run as a scene of its own, reproduce the whole scene entity for entity and, merged, its visible list."""
+    from zenyth_b200.distributed import merge_visible, shard_scene_by_roots
+    sizes = h8_geo_level_sizes(7, 5)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    arrays["parent"][sizes[0] + 5] = 0xFFFFFFFF             # a root below level 0, with its own subtree
+    view, proj = camera(oracle)
+    ref = oracle.scene_update(arrays, view, proj, threads=4)
+    lists = []
+    for shard in shard_scene_by_roots(arrays, world):
+        got = run_gpu(gpu_ctx, shard.arrays, view, proj)
+        assert same_values(got["world"], ref["world"][shard.global_index])
+        assert same_values(got["mvp"], ref["mvp"][shard.global_index])
+        lists.append(shard.to_global(got["visible"]))
+    assert np.array_equal(merge_visible(lists), ref["visible"])

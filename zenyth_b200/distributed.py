@@ -33,6 +33,115 @@ def scene_index_bases(entity_counts: Sequence[int]) -> List[int]:
     return bases
 
 
+NO_PARENT = 0xFFFFFFFF
+
+
+class SceneShard:
+    """One rank's part of a scene split by root subtree (shard_scene_by_roots).
+
+    arrays         the shard as a scene of its own: position/rotation/scale/aabb_center/aabb_half
+                   [n,3], parent [n] (shard-local indices, NO_PARENT for roots), level_offsets
+                   [levels+1] — what Scene.Load / Scene(ctx, n, level_offsets) take.  A shard that owns
+                   no entity of the deepest levels simply has fewer levels.
+    global_index   [n] ascending: the scene-wide index of every shard entity.  A shard-local visible
+                   list becomes global by global_index[visible]; because the map is monotonic the
+                   result is still ascending, so the scene-wide list is the k-way merge (or, with
+                   shard-major numbering, the concatenation) of the shards' lists.
+    """
+
+    def __init__(self, arrays: dict, global_index):
+        self.arrays, self.global_index = arrays, global_index
+
+    @property
+    def entity_count(self) -> int:
+        return int(self.global_index.size)
+
+    def to_global(self, visible_local):
+        return self.global_index[visible_local]
+
+
+def root_of_entities(level_offsets, parent):
+    """[E] scene-wide index of the root every entity hangs from (level-ordered scene: a parent
+    always lives in an earlier level, so one pass per level resolves it)."""
+    import numpy as np
+    level_offsets = np.asarray(level_offsets, np.int64)
+    parent = np.asarray(parent, np.uint32)
+    root = np.arange(parent.size, dtype=np.int64)
+    for l in range(level_offsets.size - 1):
+        lo, hi = int(level_offsets[l]), int(level_offsets[l + 1])
+        p = parent[lo:hi]
+        has = p != NO_PARENT
+        if has.any():
+            if int(p[has].max()) >= lo:
+                raise ValueError(f"level {l}: a parent index is not in an earlier level")
+            seg = root[lo:hi]
+            seg[has] = root[p[has].astype(np.int64)]
+    return root
+
+
+def shard_scene_by_roots(arrays: dict, world_size: int) -> List["SceneShard"]:
+    """Split ONE scene into `world_size` hierarchy-closed shards ("within one scene,
+    partition by root subtree, so no cross-GPU parent reads").
+
+    Roots (entities without a parent, in any level) are dealt out in index order as contiguous runs
+    whose subtree sizes balance the entity counts; every entity follows its root.  Within a shard the
+    scene-wide order is kept, so levels stay level-ordered and children stay sorted by parent — the
+    layout contract of zn_scene_set_parents holds for every shard without re-sorting.  Pure host
+    logic over numpy arrays; no arithmetic of the path.
+    """
+    import numpy as np
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    level_offsets = np.asarray(arrays["level_offsets"], np.int64)
+    E = int(level_offsets[-1])
+    parent = arrays.get("parent")
+    parent = np.full(E, NO_PARENT, np.uint32) if parent is None else np.asarray(parent, np.uint32)
+    root = root_of_entities(level_offsets, parent)
+    roots = np.flatnonzero(parent == NO_PARENT)
+    if roots.size < world_size:
+        raise ValueError(f"{roots.size} root subtrees cannot be split over {world_size} ranks")
+    subtree = np.bincount(root, minlength=E)[roots]                   # entities under every root
+    # contiguous runs of roots: root k goes to the rank its cumulative midpoint falls in, then the
+    # cut points are nudged so that no rank is left empty
+    mid = np.cumsum(subtree) - subtree / 2.0
+    owner_of_root = np.minimum((mid * world_size / float(subtree.sum())).astype(np.int64), world_size - 1)
+    owner_of_root = np.maximum.accumulate(owner_of_root)
+    cuts = np.searchsorted(owner_of_root, np.arange(1, world_size))  # first root of ranks 1..W-1
+    for r in range(world_size - 1):                                   # strictly increasing, room for the ranks behind
+        lo = (cuts[r - 1] + 1) if r else 1
+        cuts[r] = min(max(cuts[r], lo), roots.size - (world_size - 1 - r))
+    owner_of_root = np.searchsorted(cuts, np.arange(roots.size), side="right")
+    owner = np.empty(E, np.int64)
+    owner[roots] = owner_of_root
+    owner = owner[root]
+    level_of = np.searchsorted(level_offsets, np.arange(E), side="right") - 1
+    shards = []
+    for r in range(world_size):
+        mask = owner == r
+        gidx = np.flatnonzero(mask)
+        local = np.cumsum(mask) - 1                                   # scene-wide -> shard-local index
+        p = parent[gidx]
+        has = p != NO_PARENT
+        p_local = np.full(gidx.size, NO_PARENT, np.uint32)
+        p_local[has] = local[p[has].astype(np.int64)].astype(np.uint32)
+        counts = np.bincount(level_of[gidx], minlength=level_offsets.size - 1)
+        # a shard keeps the scene's level order; levels it owns nothing of are dropped (zn_scene_create
+        # rejects empty levels) — parents still live in earlier levels, which is all the contract asks
+        offs = np.concatenate([[0], np.cumsum(counts[counts > 0])]).astype(np.uint32)
+        a = {k: np.ascontiguousarray(np.asarray(arrays[k])[gidx]) for k in ("position", "rotation", "scale", "aabb_center", "aabb_half")}
+        a["parent"] = p_local
+        a["level_offsets"] = offs
+        shards.append(SceneShard(a, gidx.astype(np.uint32)))
+    return shards
+
+
+def merge_visible(lists) -> "object":
+    """Scene-wide ascending visible list from the shards' (already global, ascending) lists."""
+    import numpy as np
+    lists = [np.asarray(v, np.uint32) for v in lists]
+    return np.sort(np.concatenate(lists), kind="stable") if lists else np.empty(0, np.uint32)
+
+
 class VisibleGather:
     """Blocking all-gather of variable-length visible lists.
 
