@@ -94,7 +94,11 @@ int zn_ctx_create(int device_ordinal, zn_ctx** out_ctx) {
 	zn_ctx* c = new zn_ctx();
 	c->device = device_ordinal;
 	c->sm_count = prop.multiProcessorCount;
-	ZN_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	const cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+		delete c;
+		return zn::fail(ZN_ERR_CUDA, "zn_ctx_create: cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(e));
+	}
 	c->stream = c->own_stream;
 	*out_ctx = c;
 	return ZN_OK;

@@ -95,6 +95,7 @@ struct zn_scene {
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events; // [levels+2]
 	struct zn_pipe* pipe = nullptr;       // pipelined host frames (zn_scene_frame_host_submit/wait), lazily created
+	bool pipe_ready = false;              // false while `pipe` is only partially built
 };
 
 struct zn_mesh_tile {

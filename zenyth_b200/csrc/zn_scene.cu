@@ -579,13 +579,15 @@ struct zn_pipe {
 	uint32_t* vis[2] = {nullptr, nullptr};
 	uint32_t* cnt[2] = {nullptr, nullptr};
 	uint32_t* host_cnt = nullptr;                 // pinned [2]
-	cudaEvent_t h2d[2], repacked[2], done[2], counted[2];
+	cudaEvent_t h2d[2] = {nullptr, nullptr}, repacked[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, counted[2] = {nullptr, nullptr};
 	uint64_t submitted = 0, collected = 0;
 };
 
 static int pipe_create(zn_scene* s) {
-	if (s->pipe) return ZN_OK;
+	if (s->pipe && s->pipe_ready) return ZN_OK;
+	pipe_destroy(s);               // a half-built pipe from an earlier failed attempt
 	zn_pipe* p = new zn_pipe();
+	s->pipe = p;                   // owned by the scene from here on: a failure below cannot leak it
 	const size_t E = s->entity_count;
 	ZN_CUDA(cudaStreamCreateWithFlags(&p->up, cudaStreamNonBlocking));
 	ZN_CUDA(cudaHostAlloc(&p->host_cnt, 8, cudaHostAllocDefault));
@@ -599,7 +601,7 @@ static int pipe_create(zn_scene* s) {
 		ZN_CUDA(cudaEventCreateWithFlags(&p->done[k], cudaEventDisableTiming));
 		ZN_CUDA(cudaEventCreateWithFlags(&p->counted[k], cudaEventDisableTiming));
 	}
-	s->pipe = p;
+	s->pipe_ready = true;
 	return ZN_OK;
 }
 
@@ -610,13 +612,15 @@ static void pipe_destroy(zn_scene* s) {
 	for (int k = 0; k < 2; ++k) if (p->down[k]) cudaStreamSynchronize(p->down[k]);
 	for (int k = 0; k < 2; ++k) {
 		cudaFree(p->staging[k]); cudaFree(p->vis[k]); cudaFree(p->cnt[k]);
-		cudaEventDestroy(p->h2d[k]); cudaEventDestroy(p->repacked[k]); cudaEventDestroy(p->done[k]); cudaEventDestroy(p->counted[k]);
+		for (cudaEvent_t e : {p->h2d[k], p->repacked[k], p->done[k], p->counted[k]})
+			if (e) cudaEventDestroy(e);
 	}
 	if (p->host_cnt) cudaFreeHost(p->host_cnt);
 	if (p->up) cudaStreamDestroy(p->up);
 	for (int k = 0; k < 2; ++k) if (p->down[k]) cudaStreamDestroy(p->down[k]);
 	delete p;
 	s->pipe = nullptr;
+	s->pipe_ready = false;
 }
 
 int zn_scene_frame_host_submit(zn_scene* s, const zn_frame_host_io* io) {
