@@ -18,3 +18,10 @@ timeout 300 python bench.py --workload flat1m --no-cpu --no-e2e > gpurun_out/ben
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_$TAG.log 2>&1
 echo "ncu rc=$?"
+# one ncu --set full capture each of the dominant kernel (8th scene_level launch = level 7) and of emit
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:scene_level_kernel --launch-skip 7 --launch-count 1 \
+  -o gpurun_out/prof_${TAG}_level7 -f python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "ncu level7 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:emit_visible_kernel --launch-skip 1 --launch-count 1 \
+  -o gpurun_out/prof_${TAG}_emit -f python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e >> gpurun_out/ncu_full_$TAG.log 2>&1
+echo "ncu emit rc=$?"
