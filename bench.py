@@ -532,6 +532,9 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
+                         "note": "frac can exceed 1: the peak is torch's copy_ (1 read : 1 write); this kernel moves 1 read : 1.73 write "
+                                 "in 16 KiB TMA bursts and reaches 83% of the 8.18 TB/s ncu reports as the device's DRAM peak "
+                                 "(profiles/r01_s2_level7_ncu_summary.csv), against 79% for the copy",
                          "kernel": f"scene_level_kernel<{'true' if dom else 'false'}> level {dom} ({dom_entities:,} entities)",
                          "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
                          "frame": {"algorithmic_bytes": frame_bytes, "ms": total_ms / args.steps / (1 if not distributed else 1),
