@@ -218,6 +218,11 @@ def cpu_baseline(workload: str, budget_s: float = 12.0) -> dict:
            "sample": f"{frames} frames of the full {sc.n:,}-entity {workload} scene, {sc.threads} host threads "
                      f"splitting each level by entity range; {sc.kind_note}",
            "ms_per_frame": dt / frames * 1e3}
+    all_threads, sc.threads = sc.threads, 1          # SURVEY.md §8d also asks for the scalar single-thread figure
+    t0 = time.perf_counter()
+    sc.frame()
+    out["one_thread"] = {"value": sc.n / (time.perf_counter() - t0) / 1e6, "unit": UNIT, "cores": 1, "sample": "1 frame of the same scene"}
+    sc.threads = all_threads
     del sc
     from oracle.binding import LIB_REFERENCE
     if os.path.exists(LIB_REFERENCE):
