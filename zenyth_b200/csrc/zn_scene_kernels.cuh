@@ -280,6 +280,23 @@ __device__ __forceinline__ void scatter_warp_words(const uint4* __restrict__ w4,
 	}
 }
 
+// 1024 consecutive indices v0, v0+1, ... into out[0..1024) by one warp: what a group of four fully
+// visible tiles contributes.  Full tiles are contiguous in entity index (also across a level
+// boundary: a level whose last tile is full ends where the next one begins), so neither the masks
+// nor a scan are needed — the counts in the record header already say "all of them".
+__device__ __forceinline__ void store_run_1024(uint32_t* __restrict__ out, uint32_t v0, int lane) {
+	if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0u) {
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const uint32_t v = v0 + k * 128 + lane * 4;
+			*reinterpret_cast<uint4*>(out + k * 128 + lane * 4) = make_uint4(v, v + 1, v + 2, v + 3);
+		}
+	} else {
+#pragma unroll 8
+		for (int k = 0; k < 32; ++k) out[k * 32 + lane] = v0 + k * 32 + lane;
+	}
+}
+
 __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ totals, const uint32_t* __restrict__ masks,
                                                const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t chunks,
                                                uint32_t chunk, uint32_t index_base, uint32_t* __restrict__ visible,
@@ -294,6 +311,35 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 	for (uint32_t j = t; j < chunk; j += 256) acc += __ldcg(totals + j);
 	acc = __reduce_add_sync(0xffffffffu, acc);
 	if (lane == 0) s_part[warp] = acc;
+
+	// Culling is spatially coherent, so most chunks are entirely invisible or entirely visible, and
+	// the chunk total (accumulated by the level kernels) says so before a single mask word is read:
+	// the header is then known in closed form and the list segment is one run of 8192 indices.
+	// (Chunks whose masks this kernel must push to peers take the general path: it loads them.)
+	const uint32_t ctot = __ldcg(totals + chunk);
+	const bool pushes_masks = record_out.n > 1 && chunk * kChunkTiles < remote_tiles_below;
+	if ((ctot == 0u || ctot == uint32_t(kChunkTiles * kTile)) && !pushes_masks) {
+		__syncthreads();
+		if (warp == 0) {
+			const uint32_t base = __reduce_add_sync(0xffffffffu, (lane < 8) ? s_part[lane] : 0u);
+			if (lane < 8) {
+				const uint32_t group_off = ctot ? uint32_t(lane) * 4u * kTile : 0u;
+				for (int q = 0; q < record_out.n; ++q) record_out.ptr[q][chunks + 1u + chunk * 8u + lane] = group_off;
+			}
+			if (lane == 0) {
+				s_base = base;
+				for (int q = 0; q < record_out.n; ++q) record_out.ptr[q][chunk] = base;
+				if (chunk == chunks - 1) {
+					*visible_count = base + ctot;
+					for (int q = 0; q < record_out.n; ++q) record_out.ptr[q][chunks] = base + ctot;
+				}
+			}
+		}
+		if (ctot == 0u) return 0u;
+		__syncthreads();
+		store_run_1024(visible + s_base + uint32_t(warp) * 4u * kTile, tile_first_entity[chunk * kChunkTiles + warp * 4] + index_base, lane);
+		return ctot;
+	}
 
 	// thread t owns mask word t of the chunk: tile chunk*32 + t/8, word t%8
 	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
@@ -443,12 +489,26 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 	const uint32_t* masks = rec + record_header_words(chunks);
 	uint32_t* visible = lists + size_t(r) * list_stride;
 	const uint32_t chunk = blockIdx.x;
+	if (chunk == 0 && t == 0) counts[r] = __ldcg(rec + chunks);
+	// The header already holds every count: entry chunk+1 is the next chunk's base (or, after the
+	// last chunk, the total), and a group's count is the distance to the next group's offset.  An
+	// empty chunk or group is skipped, a full group is one run of 1024 indices — in both cases
+	// without reading a mask word.
+	const uint32_t chunk_base = __ldcg(rec + chunk);
+	const uint32_t chunk_count = __ldcg(rec + chunk + 1u) - chunk_base;
+	if (chunk_count == 0u) return;                            // CTA-uniform
 	const uint32_t group = chunk * 8u + warp;                 // 4 tiles = 32 mask words
 	const uint32_t tile = group * 4u + (lane >> 3);
-	if (tile - (lane >> 3) >= tiles) return;                  // whole group past the end (warp-uniform)
+	if (group * 4u >= tiles) return;                          // whole group past the end (warp-uniform)
+	const uint32_t group_off = __ldcg(rec + chunks + 1u + group);
+	const uint32_t group_count = (warp < 7 ? __ldcg(rec + chunks + 2u + group) : chunk_count) - group_off;
+	if (group_count == 0u) return;                            // warp-uniform
+	const uint32_t base = chunk_base + group_off;
+	if (group_count == 4u * kTile) {
+		store_run_1024(visible + base, tile_first_entity[group * 4u] + bases.base[r], lane);
+		return;
+	}
 	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
-	const uint32_t base = __ldcg(rec + chunk) + __ldcg(rec + chunks + 1u + group);
-	if (chunk == 0 && t == 0) counts[r] = __ldcg(rec + chunks);
 	const uint32_t cnt = __popc(word);
 	uint32_t incl = cnt;
 #pragma unroll
