@@ -123,8 +123,8 @@ class ClockSampler:
 
 
 class NvmlSampler:
-    """SM clock / throttle reasons polled through NVML every ~2 ms from a thread DURING the timed
-    region (the timed region is ~10 ms: nvidia-smi's 100 ms loop sees it once or twice)."""
+    """SM clock / throttle reasons polled through NVML back to back (0.5 ms pause) from a thread DURING
+    the timed region (the timed region is ~10 ms: nvidia-smi's 100 ms loop sees it once or twice)."""
 
     def __init__(self, gpu_uuid: str):
         import threading
@@ -148,7 +148,7 @@ class NvmlSampler:
                 self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def stop(self) -> dict:
         self._stop.set()
@@ -160,7 +160,7 @@ class NvmlSampler:
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "power_w_max": float(max(self.power)) if self.power else None,
-                "samples": len(self.sm), "reasons": active, "source": "NVML polled every ~2 ms during the timed region"}
+                "samples": len(self.sm), "reasons": active, "source": "NVML polled back to back (0.5 ms pause) during the timed region"}
 
 
 def make_sampler(gpu_uuid: str):
