@@ -662,25 +662,49 @@ def run_scenes8(args) -> None:
         sc.SetIndexBase(bases[sid])
         scenes.append(sc)
     words = scenes[0].DeviceBuffers().visibility_record_words
+    launches_per_update = scenes[0].LaunchesPerUpdate()
     frame_no = [0]
-    if distributed:
+    mode, fallback_note = (args.exchange if distributed else "none"), ""
+    if mode == "lists":
+        raise SystemExit("bench.py: --workload scenes8x32m exchanges visibility records (--exchange peer | records | peer-nccl | peer-waitkernel)")
+    index_bases = np.asarray(bases, np.uint32)
+    if mode.startswith("peer"):
+        from zenyth_b200.peer_exchange import PeerRecordExchange
+        try:
+            exchange = PeerRecordExchange(ctx, words, E, world_size, rank, dev, torch.int32, slots=4, records_per_rank=len(owned),
+                                          signal="nccl" if mode == "peer-nccl" else "flags", fused_wait=mode != "peer-waitkernel")
+        except RuntimeError as e:    # raised on every rank together
+            fallback_note = f" [--exchange {mode} unavailable ({e}); ran --exchange records]"
+            mode = "records"
+    use_peer = mode.startswith("peer")
+    if mode == "records":
         exchange = RecordExchange(words, E, world_size, dev, torch.int32, slots=2, records_per_rank=len(owned))
-        index_bases = np.asarray(bases, np.uint32)
 
     def step():
-        slot = frame_no[0] % 2
-        for j, sc in enumerate(scenes):
+        k = frame_no[0]
+        if use_peer:
+            exchange.bind(scenes, k)
+            for sc in scenes:
+                sc.Update()                              # kernels store the records into every peer as they run
+            exchange.launch(k)
+            exchange.expand(scenes[0], k - 1, index_bases)
+        else:
+            slot = k % 2
+            for j, sc in enumerate(scenes):
+                if distributed:
+                    sc.BindVisibilityRecord(exchange.record_ptr(slot, j))
+                sc.Update()
             if distributed:
-                sc.BindVisibilityRecord(exchange.record_ptr(slot, j))
-            sc.Update()
-        if distributed:
-            exchange.launch(slot)
-            if exchange.ready(1 - slot):
-                exchange.expand(scenes[0], 1 - slot, index_bases)
+                exchange.launch(slot)
+                if exchange.ready(1 - slot):
+                    exchange.expand(scenes[0], 1 - slot, index_bases)
         frame_no[0] += 1
 
     def finish():
-        if distributed:
+        if use_peer:
+            for k in (frame_no[0] - 2, frame_no[0] - 1):
+                exchange.expand(scenes[0], k, index_bases)
+        elif distributed:
             for slot in ((frame_no[0] - 2) % 2, (frame_no[0] - 1) % 2):
                 if exchange.ready(slot):
                     exchange.expand(scenes[0], slot, index_bases)
@@ -694,9 +718,24 @@ def run_scenes8(args) -> None:
         step()
     finish()
     barrier()
-    local_counts = [sc.VisibleCount() if not distributed else None for sc in scenes]
+    local_counts = [sc.VisibleCount() for sc in scenes]
     if distributed:
-        counts, _ = exchange.result()
+        # every rank derived all 8 lists: check counts and list checksums against the owners' own lists
+        counts, lists = exchange.result()
+
+        def checksum(t):
+            t = t.to(torch.int64) & 0xFFFFFFFF
+            return torch.stack([t.sum(), (t * (torch.arange(t.numel(), device=dev) % 1021 + 1)).sum()])
+
+        own = torch.stack([torch.cat([torch.tensor([n], dtype=torch.int64, device=dev),
+                                      checksum(torch.from_numpy(sc.Visible().astype(np.int64)).to(dev))])
+                           for sc, n in zip(scenes, local_counts)]).flatten()
+        every = torch.zeros(total_scenes * 3, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, own)
+        every = every.view(total_scenes, 3)
+        assert counts == every[:, 0].tolist(), (counts, every[:, 0].tolist())
+        for sid in range(total_scenes):
+            assert torch.equal(checksum(lists[sid, : counts[sid]]), every[sid, 1:]), f"rank {rank}: list of scene {sid} differs from its owner's"
     else:
         counts = local_counts
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -707,6 +746,8 @@ def run_scenes8(args) -> None:
     finish()
     stop.record(stream)
     barrier()
+    if use_peer:
+        exchange.close(scenes)
     ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -720,12 +761,17 @@ def run_scenes8(args) -> None:
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "8 independent H8-geo scenes of 33,554,430 entities sharded over the GPUs (BASELINE configs[4])",
                        "scenes_per_gpu": len(owned), "visible_counts": counts,
-                       "collective": "NCCL all_gather of visibility records + local expansion of all 8 lists on every rank" if distributed
-                                     else "none (1 GPU: every scene's own emit already leaves its list on the device)"},
+                       "exchange": mode,
+                       "collective": (("visibility records stored by the level/emit kernels straight into every peer's memory over NVLink "
+                                       "(CUDA IPC), completion flags in peer memory, local expansion of the peers' lists on every rank; "
+                                       "no collective in the timed region") if mode in ("peer", "peer-waitkernel") else
+                                      "peer stores of the records + a 4-byte NCCL all-reduce per frame as the barrier" if mode == "peer-nccl" else
+                                      "NCCL all_gather of visibility records + local expansion of all 8 lists on every rank" if distributed
+                                      else "none (1 GPU: every scene's own emit already leaves its list on the device)") + fallback_note},
             "roofline": {"bound": "hbm", "achieved": alg / (total_ms / args.steps * 1e-3) / 1e9 / world_size, "peak": peak, "unit": "GB/s",
                          "frac": alg / (total_ms / args.steps * 1e-3) / 1e9 / world_size / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "whole step, per GPU (algorithmic bytes of all 8 frames / step time / N)"},
-            "gpu_launches": args.steps * len(owned) * scenes[0].LaunchesPerUpdate()}), flush=True)
+            "gpu_launches": args.steps * (len(owned) * launches_per_update + (1 if distributed else 0))}), flush=True)
     for sc in scenes:
         sc.Close()
     ctx.Close()

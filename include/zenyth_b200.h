@@ -147,7 +147,9 @@ int zn_scene_expand_visible(zn_scene* scene, const void* records_dev, uint32_t r
  *     (fence.sys + st.release.sys by one thread) — and (2) whose CTAs wait (ld.acquire.sys) until
  *     flags_dev[(r / records_per_flag) * flag_stride_words] has reached `expected` for their record
  *     r, so the stream needs no host- or NCCL-side barrier.  The wait is bounded: after timeout_ms
- *     the kernel stores 1 + r into *status_dev (a zero-initialised device word) and goes on. */
+ *     the kernel stores 1 + r into *status_dev (a zero-initialised device word) and goes on.
+ *     Records [skip_index, skip_index + skip_count) are left out (a rank that owns several scenes
+ *     already has their lists); records_per_flag = scenes per rank. */
 int zn_scene_bind_peer_signal(zn_scene* scene, void* const* flag_ptrs, uint32_t flag_count);
 /* The same signal + bounded wait as a launch of its own on the context stream (all flag_count
  * flags must reach `expected`); a plain zn_scene_expand_visible may follow it. */
@@ -155,7 +157,7 @@ int zn_scene_wait_flags(zn_scene* scene, const void* flags_dev, uint32_t flag_st
                         uint32_t timeout_ms, void* status_dev);
 int zn_scene_set_signal_value(zn_scene* scene, uint32_t value);
 int zn_scene_expand_visible_signalled(zn_scene* scene, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
-                                      int skip_index, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
+                                      int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
                                       const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
                                       uint32_t timeout_ms, void* status_dev);
 /* Added to every index written to the visible list (shard -> global numbering). */

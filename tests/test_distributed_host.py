@@ -206,6 +206,24 @@ def _peer_worker(rank: int, world: int, port: int, out_dir: str):
     ok &= signal_values == [1, 2, 3, 4, 5, 6]
     ex.close(sc)
     ok &= ctx.closed == [peer] and ctx.freed == [own]
+    # (3) several scenes per rank: rank r's scene j is record r*S + j; one flag per rank covers all of them
+    ctx, a, b = _FakeCtx(rank), _FakeScene(), _FakeScene()
+    ex = PeerRecordExchange(ctx, words, cap, world, rank, "cpu", torch.int32, records_per_rank=2)
+    slot_bytes = world * 2 * words * 4
+    for k in range(3):
+        ex.bind([a, b], k)
+        a.Update(), b.Update()
+        ex.expand(a, k - 1)
+    for j, sc in enumerate((a, b)):
+        cells = [c[1][0] for c in sc.calls if c[0] == "BindVisibilityRecord"]
+        ok &= cells == [own + (k % 4) * slot_bytes + (rank * 2 + j) * words * 4 for k in range(3)]
+        outs = [c[1] for c in sc.calls if c[0] == "BindVisibleOutput"]
+        ok &= [o[0] for o in outs] == [ex.lists.data_ptr() + ((k % 2) * world * 2 + rank * 2 + j) * cap * 4 for k in range(3)]
+    ok &= [c[0] for c in b.calls].count("BindPeerSignal") == 0 and [c[0] for c in b.calls].count("SetSignalValue") == 0
+    e = [c for c in a.calls if c[0] == "ExpandVisibleSignalled"]
+    ok &= len(e) == 2 and all(c[1][1] == world * 2 for c in e)
+    ok &= all(c[2]["skip_index"] == rank * 2 and c[2]["skip_count"] == 2 and c[2]["records_per_flag"] == 2 for c in e)
+    ex.close([a, b])
     with open(os.path.join(out_dir, f"peer{rank}.ok"), "w") as f:
         f.write("1" if ok else "0")
     dist.destroy_process_group()

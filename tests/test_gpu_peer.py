@@ -126,26 +126,36 @@ ctx = zn.GpuContext(rank, stream=stream.cuda_stream)
 sizes = [7 * 8 ** l for l in range(7)]
 E = sum(sizes)
 offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
-for signal in ("flags", "nccl"):
-    sc = zn.Scene(ctx, E, offs)
-    sc.FillSynthetic(0x5A454E59 + 11 + rank, 8, 0.25)
-    sc.SetCamera(zn.Camera(zn.CameraDesc(eye=(0, 0, 1500.0), center=(0, 0, 1499.0))))
-    sc.SetIndexBase(rank * E)
-    sc.Update()
-    mine = sc.Visible().astype(np.int64)
-    ex = PeerRecordExchange(ctx, sc.DeviceBuffers().visibility_record_words, E, world, rank, dev, torch.int32, signal=signal)
-    bases = np.arange(world, dtype=np.uint32) * E
+for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2)):
+    scenes, mine = [], []
+    for j in range(S):
+        sc = zn.Scene(ctx, E, offs)
+        sc.FillSynthetic(0x5A454E59 + 11 + rank * S + j, 8, 0.25)
+        sc.SetCamera(zn.Camera(zn.CameraDesc(eye=(0, 0, 1500.0), center=(0, 0, 1499.0))))
+        sc.SetIndexBase((rank * S + j) * E)
+        sc.Update()
+        mine.append(sc.Visible().astype(np.int64))
+        scenes.append(sc)
+    ex = PeerRecordExchange(ctx, scenes[0].DeviceBuffers().visibility_record_words, E, world, rank, dev, torch.int32, signal=signal,
+                            records_per_rank=S)
+    bases = np.arange(world * S, dtype=np.uint32) * E
     for k in range(9):
-        ex.bind(sc, k); sc.Update(); ex.launch(k); ex.expand(sc, k - 1, bases)
-    ex.expand(sc, 8, bases)
+        ex.bind(scenes, k)
+        for sc in scenes:
+            sc.Update()
+        ex.launch(k)
+        ex.expand(scenes[0], k - 1, bases)
+    ex.expand(scenes[0], 8, bases)
     counts, lists = ex.result()
     every = [None] * world
     dist.all_gather_object(every, mine)
-    for r in range(world):
-        assert counts[r] == every[r].size, (signal, r, counts, every[r].size)
-        assert np.array_equal(lists[r, :counts[r]].cpu().numpy().astype(np.int64) & 0xFFFFFFFF, every[r]), (signal, r)
-    ex.close(sc)
-    sc.Close()
+    every = [v for per_rank in every for v in per_rank]
+    for r in range(world * S):
+        assert counts[r] == every[r].size, (signal, S, r, counts, every[r].size)
+        assert np.array_equal(lists[r, :counts[r]].cpu().numpy().astype(np.int64) & 0xFFFFFFFF, every[r]), (signal, S, r)
+    ex.close(scenes)
+    for sc in scenes:
+        sc.Close()
 ctx.Close()
 dist.destroy_process_group()
 print("peer exchange ok", rank)

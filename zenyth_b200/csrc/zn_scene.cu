@@ -298,7 +298,7 @@ int zn_scene_set_signal_value(zn_scene* s, uint32_t value) {
 }
 
 static int expand_visible(zn_scene* s, const char* who, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
-                          int skip_index, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
+                          int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
                           const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
                           uint32_t timeout_ms, void* status_dev) {
 	ZN_REQUIRE(s && records_dev && lists_dev && counts_dev, "%s: NULL argument", who);
@@ -314,7 +314,7 @@ static int expand_visible(zn_scene* s, const char* who, const void* records_dev,
 		sig.value = s->signal_value;
 	}
 	expand_visible_kernel<<<dim3(s->chunk_count, record_count), 256, 0, s->ctx->stream>>>(
-		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, skip_index,
+		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, skip_index, int(skip_count),
 		static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),
 		static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag, uint64_t(timeout_ms) * 1000000ull,
 		static_cast<uint32_t*>(status_dev), sig);
@@ -324,17 +324,18 @@ static int expand_visible(zn_scene* s, const char* who, const void* records_dev,
 
 int zn_scene_expand_visible(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
                             const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev) {
-	return expand_visible(s, "zn_scene_expand_visible", records_dev, record_count, record_stride_words, skip_index, index_bases, lists_dev,
+	return expand_visible(s, "zn_scene_expand_visible", records_dev, record_count, record_stride_words, skip_index, 1, index_bases, lists_dev,
 	                      list_stride, counts_dev, nullptr, 0, 1, 0, 0, nullptr);
 }
 
 int zn_scene_expand_visible_signalled(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
-                                      const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
+                                      uint32_t skip_count, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
                                       const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
                                       uint32_t timeout_ms, void* status_dev) {
 	ZN_REQUIRE(flags_dev && status_dev, "zn_scene_expand_visible_signalled: flags_dev / status_dev is NULL");
 	ZN_REQUIRE(records_per_flag >= 1 && timeout_ms >= 1, "zn_scene_expand_visible_signalled: records_per_flag and timeout_ms must be >= 1");
-	return expand_visible(s, "zn_scene_expand_visible_signalled", records_dev, record_count, record_stride_words, skip_index, index_bases,
+	ZN_REQUIRE(skip_count <= record_count, "zn_scene_expand_visible_signalled: skip_count %u > record_count %u", skip_count, record_count);
+	return expand_visible(s, "zn_scene_expand_visible_signalled", records_dev, record_count, record_stride_words, skip_index, skip_count, index_bases,
 	                      lists_dev, list_stride, counts_dev, flags_dev, flag_stride_words, records_per_flag, expected, timeout_ms, status_dev);
 }
 

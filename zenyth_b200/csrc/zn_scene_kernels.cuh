@@ -452,7 +452,7 @@ struct ExpandBases {
 // shared-memory reduction, no block barrier.
 __global__ void __launch_bounds__(256)
 expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
-                      uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, int skip,
+                      uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, int skip, int skip_count,
                       uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ counts,
                       const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t expected, uint32_t records_per_flag,
                       uint64_t timeout_ns, uint32_t* __restrict__ status, const __grid_constant__ SignalTargets sig) {
@@ -465,7 +465,7 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 		__threadfence_system();
 		for (int q = 0; q < sig.n; ++q) st_release_sys(sig.flag[q], sig.value);
 	}
-	if (int(r) == skip) return;
+	if (int(r) >= skip && int(r) < skip + skip_count) return;   // records whose lists the caller already has (its own scenes')
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	if (flags) {
 		// Record r was stored into this GPU's memory by its owner's kernels (SignalTargets above): wait

@@ -271,11 +271,12 @@ class Scene:
 
     def ExpandVisibleSignalled(self, records_ptr: int, record_count: int, record_stride_words: int, lists_ptr: int, list_stride: int,
                                counts_ptr: int, flags_ptr: int, flag_stride_words: int, expected: int, status_ptr: int,
-                               index_bases=None, skip_index: int = -1, records_per_flag: int = 1, timeout_ms: int = 2000) -> None:
+                               index_bases=None, skip_index: int = -1, skip_count: int = 1, records_per_flag: int = 1,
+                               timeout_ms: int = 2000) -> None:
         """ExpandVisible whose CTAs first wait for the owners' flags (zn_scene_expand_visible_signalled)."""
         bases = None if index_bases is None else np.ascontiguousarray(index_bases, np.uint32)
         check(self._lib.zn_scene_expand_visible_signalled(
-            self._h, C.c_void_p(records_ptr), record_count, record_stride_words, skip_index, _p(bases), C.c_void_p(lists_ptr),
+            self._h, C.c_void_p(records_ptr), record_count, record_stride_words, skip_index, skip_count, _p(bases), C.c_void_p(lists_ptr),
             list_stride, C.c_void_p(counts_ptr), C.c_void_p(flags_ptr), flag_stride_words, records_per_flag, expected & 0xFFFFFFFF,
             timeout_ms, C.c_void_p(status_ptr)))
 
