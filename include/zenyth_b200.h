@@ -86,6 +86,19 @@ void zn_mat4_mul(const float a[16], const float b[16], float out[16]);
 /* Six planes (nx,ny,nz,d) from the rows of view_proj: left,right,bottom,top,near,far. */
 void zn_frustum_planes(const float view_proj[16], float out_planes[24]);
 
+/* ---- hierarchy layout (host only, no device needed): entities in creation order, each naming its
+ *      parent (ZN_NO_PARENT for roots), to the order the scene calls below require — level by level,
+ *      a parent always in an earlier level, the children of a level sorted by parent, siblings in
+ *      their original relative order.  The reference has no Scene to take an order from; this is
+ *      what a Scene::AddEntity / SetParent pair would maintain.
+ *        out_order[new]            original index of the entity now at `new`     [count]
+ *        out_parent[new]           its parent's NEW index, or ZN_NO_PARENT        [count], may be NULL
+ *        out_level_offsets[0..L]   level l is [offsets[l], offsets[l+1])          needs L+1 <= level_capacity
+ *        *out_level_count          L (also set when level_capacity was too small, so a caller can retry)
+ *      Fails with ZN_ERR_INVALID on a parent index out of range, a self-parent or a cycle. ---- */
+int zn_hierarchy_sort(const uint32_t* parent, uint32_t count, uint32_t* out_order, uint32_t* out_parent,
+                      uint32_t* out_level_offsets, uint32_t level_capacity, uint32_t* out_level_count);
+
 /* ---- scene: TRS -> world over the hierarchy, MVP, AABB-vs-frustum cull + ordered compaction.
  *      Called from where Application::OnUpdate(dt) and OnRender() run
  *      (Core/src/Application.cpp:47,50). ---- */

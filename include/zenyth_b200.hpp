@@ -120,6 +120,32 @@ private:
 	zn_ctx* m_ctx = nullptr;
 };
 
+// Entities in creation order, each naming its parent (ZN_NO_PARENT for roots), to the level-ordered,
+// sorted-by-parent layout Scene requires.  order[new] = original index; per-entity arrays follow it.
+struct HierarchyLayout {
+	std::vector<uint32_t> order;          // [count] new index -> original index
+	std::vector<uint32_t> parent;         // [count] parents as NEW indices
+	std::vector<uint32_t> levelOffsets;   // [levels + 1], what SceneDesc::levelOffsets takes
+};
+[[nodiscard]] inline HierarchyLayout SortHierarchy(const std::vector<uint32_t>& parent) {
+	HierarchyLayout out;
+	const uint32_t n = static_cast<uint32_t>(parent.size());
+	out.order.resize(n);
+	out.parent.resize(n);
+	out.levelOffsets.resize(66);
+	uint32_t levels = 0;
+	int rc = zn_hierarchy_sort(parent.data(), n, out.order.data(), out.parent.data(), out.levelOffsets.data(),
+	                           static_cast<uint32_t>(out.levelOffsets.size()), &levels);
+	if (rc != ZN_OK && levels + 1 > out.levelOffsets.size()) {   // deeper than guessed: retry with the count that came back
+		out.levelOffsets.resize(levels + 1);
+		rc = zn_hierarchy_sort(parent.data(), n, out.order.data(), out.parent.data(), out.levelOffsets.data(),
+		                       static_cast<uint32_t>(out.levelOffsets.size()), &levels);
+	}
+	detail::Check(rc, "SortHierarchy");
+	out.levelOffsets.resize(levels + 1);
+	return out;
+}
+
 struct SceneDesc {
 	uint32_t entityCount = 0;
 	std::vector<uint32_t> levelOffsets;   // empty = one level of roots

@@ -349,3 +349,27 @@ def test_one_scene_sharded_by_root_subtree(oracle, gpu_ctx, world):
         assert same_values(got["mvp"], ref["mvp"][shard.global_index])
         lists.append(shard.to_global(got["visible"]))
     assert np.array_equal(merge_visible(lists), ref["visible"])
+
+
+def test_scene_given_in_creation_order(oracle, gpu_ctx):
+    """An engine's entities in arbitrary order: zn_hierarchy_sort lays them out, the GPU scene then
+    matches the oracle entity for entity (mapped back through `order`)."""
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 4)
+    arrays = oracle.synth_scene(BASE_SEED + 17, sizes, fanout=8, center_range=0.25)
+    view, proj = camera(oracle)
+    ref = oracle.scene_update(arrays, view, proj, threads=4)
+    rng = np.random.default_rng(5)
+    n = sum(sizes)
+    new_of_old = rng.permutation(n).astype(np.uint32)            # shuffle into "creation order"
+    old_of_new = np.argsort(new_of_old).astype(np.uint32)
+    p = arrays["parent"][old_of_new]
+    created_parent = np.where(p == 0xFFFFFFFF, 0xFFFFFFFF, new_of_old[np.minimum(p, n - 1)]).astype(np.uint32)
+    order, new_parent, offsets = zn.SortHierarchy(created_parent)
+    assert np.array_equal(np.diff(offsets), sizes)
+    pick = old_of_new[order]                                      # index in `arrays` of every sorted entity
+    laid_out = {k: np.ascontiguousarray(arrays[k][pick]) for k in ("position", "rotation", "scale", "aabb_center", "aabb_half")}
+    laid_out.update(parent=new_parent, level_offsets=offsets)
+    got = run_gpu(gpu_ctx, laid_out, view, proj)
+    assert same_values(got["world"], ref["world"][pick]) and same_values(got["mvp"], ref["mvp"][pick])
+    assert np.array_equal(np.sort(pick[got["visible"]]), ref["visible"])

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "zn_mat4_perspective_reverse_z": (None, [C.c_float, C.c_float, C.c_float, vp]),
     "zn_mat4_mul": (None, [vp, vp, vp]),
     "zn_frustum_planes": (None, [vp, vp]),
+    "zn_hierarchy_sort": (C.c_int, [vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
     "zn_scene_create": (C.c_int, [vp, C.POINTER(SceneDesc), C.POINTER(vp)]),
     "zn_scene_destroy": (C.c_int, [vp]),
     "zn_scene_set_transforms": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_size_t]),

@@ -15,7 +15,7 @@ import numpy as np
 from . import _capi
 from ._capi import ZN_NO_PARENT, ZenythError, check
 
-__all__ = ["GpuContext", "Transform", "CameraDesc", "Camera", "Scene", "Mesh", "mat4", "ZN_NO_PARENT", "ZenythError"]
+__all__ = ["GpuContext", "Transform", "CameraDesc", "Camera", "Scene", "Mesh", "mat4", "SortHierarchy", "ZN_NO_PARENT", "ZenythError"]
 
 
 def _f32(a, shape=None):
@@ -68,6 +68,27 @@ class mat4:
         out = np.zeros(24, np.float32)
         _capi.load().zn_frustum_planes(_p(_f32(view_proj, 16)), _p(out))
         return out.reshape(6, 4)
+
+
+def SortHierarchy(parent):
+    """Entities in creation order (parent[e] = index of e's parent, ZN_NO_PARENT for roots) ->
+    (order, new_parent, level_offsets): the level-ordered, sorted-by-parent layout the Scene calls
+    require (zn_hierarchy_sort; host only, no GPU).  Per-entity arrays go along as array[order]."""
+    lib = _capi.load()
+    parent = np.ascontiguousarray(parent, np.uint32)
+    n = int(parent.size)
+    order = np.empty(n, np.uint32)
+    new_parent = np.empty(n, np.uint32)
+    levels = C.c_uint32(0)
+    capacity = 66
+    while True:
+        offsets = np.empty(capacity, np.uint32)
+        rc = lib.zn_hierarchy_sort(_p(parent), n, _p(order), _p(new_parent), _p(offsets), capacity, C.byref(levels))
+        if rc != 0 and levels.value + 1 > capacity:      # deeper than guessed: the count came back, retry once
+            capacity = levels.value + 1
+            continue
+        check(rc)
+        return order, new_parent, offsets[: levels.value + 1].copy()
 
 
 class GpuContext:
