@@ -528,7 +528,7 @@ def run_ours(args) -> None:
                             "ends after the last expansion; --exchange lists runs the literal list all-gather") if use_records else
                            ("fused into the compute kernels over NVLink peer memory, no collective: the level and emit kernels store "
                             "the visibility record tile by tile into every peer's buffer (CUDA IPC mapped pointers); "
-                            + ("the emit kernel's last CTA raises a sequence flag at every peer (fence.sys + st.release.sys) and the "
+                            + ("the kernel that follows the update on the stream raises a sequence flag at every peer (one fence.sys + relaxed sys-scope stores) and the "
                                "expansion kernel waits on the owners' flags itself — no NCCL call in the timed region; "
                                if mode != "peer-nccl" else "a 4-byte NCCL all-reduce per frame is the cross-rank barrier; ")
                             + "every rank expands its peers' records into the ordered index lists + counts (its own list comes "

@@ -157,7 +157,7 @@ int zn_scene_expand_visible(zn_scene* scene, const void* records_dev, uint32_t r
  *     (compared as a signed 32-bit distance, so it may wrap).
  *   expand_visible_signalled: zn_scene_expand_visible that (1) first raises the bound flags to the
  *     signal value — every update enqueued before it is complete by then, peer stores included
- *     (fence.sys + st.release.sys by one thread) — and (2) whose CTAs wait (ld.acquire.sys) until
+ *     (one fence.sys, then relaxed system-scope stores, by one thread) — and (2) whose CTAs wait (ld.acquire.sys) until
  *     flags_dev[(r / records_per_flag) * flag_stride_words] has reached `expected` for their record
  *     r, so the stream needs no host- or NCCL-side barrier.  The wait is bounded: after timeout_ms
  *     the kernel stores 1 + r into *status_dev (a zero-initialised device word) and goes on.

@@ -74,8 +74,12 @@ struct SignalTargets {
 	uint32_t value;
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Raise every flag of `sig` to its value: ONE system-scope fence (everything this thread has
+// observed — the completed update before this kernel on the stream — is ordered before the flags),
+// then relaxed system-scope stores.  (st.release.sys per flag compiles to a MEMBAR.ALL.SYS each.)
+__device__ __forceinline__ void raise_flags(const SignalTargets& sig) {
+	__threadfence_system();
+	for (int q = 0; q < sig.n; ++q) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sig.flag[q]), "r"(sig.value) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 	uint32_t v;
@@ -426,10 +430,7 @@ emit_visible_kernel(const __grid_constant__ RecordTargets rec, const uint32_t* _
 __global__ void wait_flags_kernel(const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t count, uint32_t expected,
                                   uint64_t timeout_ns, uint32_t* __restrict__ status, const __grid_constant__ SignalTargets sig) {
 	const uint32_t r = threadIdx.x;
-	if (r == 0 && sig.n > 0) {
-		__threadfence_system();
-		for (int q = 0; q < sig.n; ++q) st_release_sys(sig.flag[q], sig.value);
-	}
+	if (r == 0 && sig.n > 0) raise_flags(sig);
 	if (r >= count) return;
 	const uint64_t t0 = global_timer_ns();
 	while (int32_t(ld_acquire_sys(flags + size_t(r) * flag_stride) - expected) < 0) {
@@ -462,8 +463,7 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 	const uint32_t r = blockIdx.y;
 	if (sig.n > 0 && blockIdx.x == 0 && r == 0 && threadIdx.x == 0) {
 		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank
-		__threadfence_system();
-		for (int q = 0; q < sig.n; ++q) st_release_sys(sig.flag[q], sig.value);
+		raise_flags(sig);
 	}
 	if (int(r) >= skip && int(r) < skip + skip_count) return;   // records whose lists the caller already has (its own scenes')
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
