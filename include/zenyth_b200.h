@@ -115,7 +115,11 @@ int zn_scene_destroy(zn_scene* scene);
 /* Host -> device upload of entities [first, first+count).  Each array is `count` records of
  * three floats, `stride_bytes` apart (12 for packed float[3], 16 for arrays of the reference's
  * 16-byte zenyth::math::vec3, Core/include/math/vector.hpp:69-72).  NULL arrays are skipped.
- * rotation = (pitch, yaw, roll) radians as mat4::from_euler (matrix.hpp:24). */
+ * rotation = (pitch, yaw, roll) radians as mat4::from_euler (matrix.hpp:24).
+ * Buffer lifetime: these two calls return once the copies are ENQUEUED on the context stream.
+ * Pageable arrays are staged by the driver before the call returns and may be reused at once;
+ * page-locked arrays (zn_host_alloc) are read by the DMA engine later and must stay untouched until
+ * the stream has passed the copy (zn_ctx_sync, or any synchronising read-back). */
 int zn_scene_set_transforms(zn_scene* scene, uint32_t first, uint32_t count,
                             const float* position, const float* rotation, const float* scale, size_t stride_bytes);
 int zn_scene_set_bounds(zn_scene* scene, uint32_t first, uint32_t count,
@@ -160,12 +164,19 @@ int zn_scene_expand_visible(zn_scene* scene, const void* records_dev, uint32_t r
  *     (one fence.sys, then relaxed system-scope stores, by one thread) — and (2) whose CTAs wait (ld.acquire.sys) until
  *     flags_dev[(r / records_per_flag) * flag_stride_words] has reached `expected` for their record
  *     r, so the stream needs no host- or NCCL-side barrier.  The wait is bounded: after timeout_ms
- *     the kernel stores 1 + r into *status_dev (a zero-initialised device word) and goes on.
+ *     the kernel stores 1 + r into *status_dev (a zero-initialised device word; the first failure
+ *     wins), does NOT expand record r (a record whose owner never signalled may be half written) and
+ *     sets counts_dev[r] = 0; the other records are expanded as usual.
+ *   NOTE: zn_scene_update never raises a flag itself — the flags of frame k go up in the NEXT
+ *     zn_scene_expand_visible_signalled / zn_scene_wait_flags launch on the stream, so the last frame
+ *     of a run must be followed by one more such call or its peers wait for the timeout.
  *     Records [skip_index, skip_index + skip_count) are left out (a rank that owns several scenes
  *     already has their lists); records_per_flag = scenes per rank. */
 int zn_scene_bind_peer_signal(zn_scene* scene, void* const* flag_ptrs, uint32_t flag_count);
 /* The same signal + bounded wait as a launch of its own on the context stream (all flag_count
- * flags must reach `expected`); a plain zn_scene_expand_visible may follow it. */
+ * flags must reach `expected`); a plain zn_scene_expand_visible may follow it.  If the wait times
+ * out (*status_dev = 1 + the flag's index), the next zn_scene_expand_visible on this scene expands
+ * nothing and zeroes its counts. */
 int zn_scene_wait_flags(zn_scene* scene, const void* flags_dev, uint32_t flag_stride_words, uint32_t flag_count, uint32_t expected,
                         uint32_t timeout_ms, void* status_dev);
 int zn_scene_set_signal_value(zn_scene* scene, uint32_t value);
@@ -176,8 +187,33 @@ int zn_scene_expand_visible_signalled(zn_scene* scene, const void* records_dev, 
 /* Added to every index written to the visible list (shard -> global numbering). */
 int zn_scene_set_index_base(zn_scene* scene, uint32_t index_base);
 
-/* One frame, asynchronous on the context stream: world[E], mvp[E], visible list + count. */
+/* One frame, asynchronous on the context stream: world[E], mvp[E], visible list + count — the
+ * fused form, for the camera given to zn_scene_set_camera.  A scene that has no camera (none set
+ * yet, or zn_scene_clear_camera) runs the world-only form below instead. */
 int zn_scene_update(zn_scene* scene);
+
+/* Update and cull as the two calls the reference's frame loop has room for: Scene::Update(dt) from
+ * Application::OnUpdate (Core/src/Application.cpp:47) and Scene::Cull(camera) from OnRender, between
+ * IRenderer::BeginFrame and EndFrame (Application.cpp:49-51).
+ *   zn_scene_update_world: TRS -> world over the hierarchy only (no camera involved): reads 40 B and
+ *     writes 64 B per entity; MVPs, masks and the visible list are left as they were.
+ *   zn_scene_cull: one camera pass over the world matrices of the last update (fused or world-only):
+ *     MVP = (proj*view)*world, AABB-vs-frustum, ordered compaction — 152 B per entity + 4 B per
+ *     visible index, no sincos, no world matrix rewritten.  May be called any number of times per
+ *     frame (main view, shadow views, a camera that moved between OnUpdate and OnRender); the result
+ *     of each call equals a fused zn_scene_update with that camera bit for bit.  `out` redirects
+ *     this pass's results into caller-owned DEVICE memory (NULL, or NULL members: the scene's own
+ *     MVP array / currently bound visible list + count); the camera of zn_scene_set_camera is not
+ *     changed.  The visibility record (and bound peer records) are rewritten by every pass. */
+typedef struct zn_cull_output {
+	void* mvp_dev;            /* float[entity_count][16], 16-byte aligned, or NULL */
+	void* visible_dev;        /* uint32[visible_capacity] or NULL (then visible_count_dev must be NULL too) */
+	uint32_t visible_capacity;/* >= entity_count */
+	void* visible_count_dev;  /* uint32[1] */
+} zn_cull_output;
+int zn_scene_update_world(zn_scene* scene);
+int zn_scene_cull(zn_scene* scene, const float view[16], const float proj[16], const zn_cull_output* out);
+int zn_scene_clear_camera(zn_scene* scene);
 
 /* Results.  These synchronise the stream. */
 int zn_scene_visible_count(zn_scene* scene, uint32_t* out_count);
@@ -247,6 +283,8 @@ int zn_scene_launches_per_update(zn_scene* scene, uint32_t* out_launches);
  * of the scan+emit tail (out_tail_ms, may be NULL).  Synchronises. */
 int zn_scene_set_profiling(zn_scene* scene, int enable);
 int zn_scene_level_times(zn_scene* scene, float* out_ms, uint32_t capacity, float* out_tail_ms);
+/* With profiling enabled: device time of the LAST zn_scene_cull's cull kernel and of its emit kernel. */
+int zn_scene_cull_times(zn_scene* scene, float* out_cull_ms, float* out_emit_ms);
 
 /* Scene ingest: a minimal binary SoA dump (the reference has no on-disk format).  Little-endian:
  * "ZNSCENE1", uint32 entity_count, uint32 level_count, uint32 level_offsets[level_count+1], then
@@ -254,6 +292,64 @@ int zn_scene_level_times(zn_scene* scene, float* out_ms, uint32_t capacity, floa
  * uint32 parent[E] — 64 bytes per entity.  zn_scene_load creates the scene it reads. */
 int zn_scene_save(zn_scene* scene, const char* path);
 int zn_scene_load(zn_ctx* ctx, const char* path, zn_scene** out_scene);
+
+/* ---- multi-GPU host layer (one process per GPU).  Host logic only — the data path
+ *      is the kernels' own peer stores; no collective library is involved.
+ *
+ *      Sharding.  Independent scenes are dealt out as contiguous blocks (zn_shard_scenes: 8 scenes over
+ *      1/2/4/8 GPUs -> 8/4/2/1 per GPU) and numbered globally by zn_scene_index_bases (exclusive prefix
+ *      sum of the entity counts -> zn_scene_set_index_base).  ONE scene is split into hierarchy-closed
+ *      entity shards by root subtree (zn_shard_scene_by_roots): roots are dealt out in index order as
+ *      contiguous runs balanced by subtree size, every entity follows its root and keeps its relative
+ *      order, so each shard is level-ordered and sorted by parent as it stands and no parent is ever
+ *      read across GPUs.  out_owner[e] = rank of entity e, out_local_index[e] = its index inside that
+ *      shard, out_shard_counts[r] = entities of shard r. ---- */
+int zn_shard_scenes(uint32_t num_scenes, uint32_t world_size, uint32_t rank, uint32_t* out_first, uint32_t* out_count);
+int zn_scene_index_bases(const uint32_t* entity_counts, uint32_t num_scenes, uint32_t* out_bases);
+int zn_shard_scene_by_roots(const uint32_t* level_offsets, uint32_t level_count, const uint32_t* parent /* may be NULL: all roots */,
+                            uint32_t world_size, uint32_t* out_owner, uint32_t* out_local_index, uint32_t* out_shard_counts);
+
+/*      The per-frame exchange: every rank ends up with every rank's compacted visible list and count.
+ *      Records travel inside the compute kernels (zn_scene_bind_peer_records), completion as flags in
+ *      peer memory (zn_scene_bind_peer_signal), a rank's own lists come straight from its emit kernels
+ *      (zn_scene_bind_visible_output) and only the peers' records are expanded.  The object below owns
+ *      the buffers (records[slots][world*S][record_words] + flags, lists[2][world*S][capacity],
+ *      counts, status) and performs the binding arithmetic; see zn_exchange.cpp for the slot-reuse
+ *      argument.  `allgather` is the one thing the caller supplies: a blocking HOST all-gather among
+ *      the ranks (every rank contributes `bytes` bytes, receives world_size*bytes in rank order; return
+ *      0 on success) — MPI_Allgather, a socket, torch.distributed.  It is used by create (twice:
+ *      handles, then "everyone mapped") and destroy (twice) only, never per frame; create and destroy
+ *      are therefore collective calls.  If any rank cannot allocate, export or map, EVERY rank's
+ *      create fails with ZN_ERR_CUDA.
+ *        per frame k:  zn_exchange_bind(x, scenes, S, k);  zn_scene_update(scenes[j]) for all j;
+ *                      zn_exchange_expand(x, scenes[0], k - 1, index_bases);
+ *        at the end:   zn_exchange_expand(x, scenes[0], last, ...) — also raises the last frame's flags.
+ *      zn_exchange_expand of a frame that was never bound (k - 1 = -1) or is already expanded is a
+ *      no-op.  index_bases[world*S] (host, may be NULL) is added to each record's indices.
+ *      zn_exchange_result synchronises the stream and returns the counts of the LAST expanded frame
+ *      and the device address + stride (in indices) of its lists: list r is lists[r*stride ..).  It
+ *      fails with ZN_ERR_STATE if a peer never signalled within timeout_ms (that record was not
+ *      expanded; the message names the rank). */
+typedef struct zn_exchange zn_exchange;
+typedef int (*zn_allgather_fn)(void* user, const void* send, void* recv, size_t bytes);
+typedef struct zn_exchange_desc {
+	uint32_t world_size;
+	uint32_t rank;
+	uint32_t records_per_rank;  /* S: scenes this rank owns (the same on every rank) */
+	uint32_t record_words;      /* zn_scene_buffers.visibility_record_words (one level layout for all scenes) */
+	uint32_t list_capacity;     /* entities per scene */
+	uint32_t slots;             /* 0 = 4, the minimum */
+	uint32_t timeout_ms;        /* 0 = 2000 */
+	zn_allgather_fn allgather;  /* may be NULL when world_size == 1 */
+	void* user;
+} zn_exchange_desc;
+int zn_exchange_create(zn_ctx* ctx, const zn_exchange_desc* desc, zn_exchange** out_exchange);
+int zn_exchange_destroy(zn_exchange* exchange, zn_scene* const* scenes, uint32_t scene_count); /* unbinds the scenes first */
+int zn_exchange_unbind(zn_exchange* exchange, zn_scene* const* scenes, uint32_t scene_count);
+int zn_exchange_bind(zn_exchange* exchange, zn_scene* const* scenes, uint32_t scene_count, uint64_t frame);
+int zn_exchange_expand(zn_exchange* exchange, zn_scene* scene, int64_t frame, const uint32_t* index_bases);
+int zn_exchange_result(zn_exchange* exchange, uint32_t* out_counts, void** out_lists_dev, uint32_t* out_list_stride);
+int zn_exchange_info(zn_exchange* exchange, uint32_t* out_total_records, uint32_t* out_list_capacity, uint64_t* out_peer_bytes_per_frame);
 
 /* ---- mesh batch: bulk vertex position / normal transform by per-instance model matrices.
  *      pos' = model.transform_point(pos); nrm' = normalize(model.inverse_transpose().transform_normal(nrm))

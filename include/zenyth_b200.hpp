@@ -205,8 +205,20 @@ public:
 	}
 	void SetIndexBase(uint32_t base) { detail::Check(zn_scene_set_index_base(m_scene, base), "Scene::SetIndexBase"); }
 
-	// One frame, asynchronous: world matrices over the hierarchy, MVP, visible list.
+	// One frame, asynchronous: world matrices over the hierarchy, MVP, visible list (the fused form,
+	// for the camera of SetCamera; a scene without a camera runs UpdateWorld instead).
 	void Update() { detail::Check(zn_scene_update(m_scene), "Scene::Update"); }
+	// The two calls the reference's frame loop has room for (Core/src/Application.cpp:47 and :49-51):
+	// UpdateWorld() from OnUpdate(dt) composes TRS -> world over the hierarchy; Cull(camera) from
+	// OnRender derives MVPs and the ordered visible list for one view from those world matrices.
+	// Cull may run for any number of cameras per frame; each result equals a fused Update with that
+	// camera bit for bit.  CullInto redirects one pass into caller-owned device memory.
+	void UpdateWorld() { detail::Check(zn_scene_update_world(m_scene), "Scene::UpdateWorld"); }
+	void Cull(const Camera& camera) { detail::Check(zn_scene_cull(m_scene, camera.View().m, camera.Proj().m, nullptr), "Scene::Cull"); }
+	void CullInto(const Camera& camera, const zn_cull_output& out) {
+		detail::Check(zn_scene_cull(m_scene, camera.View().m, camera.Proj().m, &out), "Scene::CullInto");
+	}
+	void ClearCamera() { detail::Check(zn_scene_clear_camera(m_scene), "Scene::ClearCamera"); }
 
 	// The all-in-one frame a CPU engine swaps in: uploads the packed host arrays that are not null,
 	// updates, downloads what is asked for; returns the visible count after the data has landed.

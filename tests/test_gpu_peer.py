@@ -98,6 +98,10 @@ def test_a_signal_that_never_comes_times_out_instead_of_hanging(oracle, gpu_ctx)
     gpu_ctx.Sync()
     assert status.item() == 2                                                 # 1 + the silent rank
     assert counts[0].item() == expect.size
+    # the record whose owner never signalled is NOT expanded (it may be half written): count 0, list untouched
+    assert counts[1].item() == 0
+    assert int(lists[E:].abs().sum().item()) == 0
+    assert np.array_equal(lists[:expect.size].cpu().numpy().astype(np.uint32), expect)
     # a flag already AHEAD of the expected sequence number passes at once
     flags[32] = 5
     status.zero_()

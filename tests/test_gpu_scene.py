@@ -150,7 +150,7 @@ def test_errors_are_loud(gpu_ctx):
     import zenyth_b200 as zn
     sc = zn.Scene(gpu_ctx, 16)
     with pytest.raises(zn.ZenythError):
-        sc.Update()   # no camera
+        sc.Cull(zn.Camera())   # no world matrices yet
     with pytest.raises(zn.ZenythError):
         sc.SetParents(np.array([3], np.uint32), first=0)   # parent not in an earlier level
     with pytest.raises(zn.ZenythError):

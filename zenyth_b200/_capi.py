@@ -38,12 +38,24 @@ class FrameHostIO(C.Structure):
                 ("visible_count", C.c_uint32)]
 
 
+class CullOutput(C.Structure):
+    _fields_ = [("mvp_dev", vp), ("visible_dev", vp), ("visible_capacity", C.c_uint32), ("visible_count_dev", vp)]
+
+
 class MeshDesc(C.Structure):
     _fields_ = [("vertex_count", C.c_uint32), ("instance_count", C.c_uint32), ("instance_first_vertex", vp)]
 
 
 class MeshBuffers(C.Structure):
     _fields_ = [("position_in", vp), ("normal_in", vp), ("position_out", vp), ("normal_out", vp), ("vertex_count", C.c_uint32)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, vp, vp, vp, C.c_size_t)
+
+
+class ExchangeDesc(C.Structure):
+    _fields_ = [("world_size", C.c_uint32), ("rank", C.c_uint32), ("records_per_rank", C.c_uint32), ("record_words", C.c_uint32),
+                ("list_capacity", C.c_uint32), ("slots", C.c_uint32), ("timeout_ms", C.c_uint32), ("allgather", ALLGATHER_FN), ("user", vp)]
 
 
 # symbol -> (restype, argtypes).  tests/test_abi.py checks this table against include/zenyth_b200.h.
@@ -88,6 +100,10 @@ PROTOTYPES = {
                                                     vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
     "zn_scene_set_index_base": (C.c_int, [vp, C.c_uint32]),
     "zn_scene_update": (C.c_int, [vp]),
+    "zn_scene_update_world": (C.c_int, [vp]),
+    "zn_scene_cull": (C.c_int, [vp, vp, vp, C.POINTER(CullOutput)]),
+    "zn_scene_clear_camera": (C.c_int, [vp]),
+    "zn_scene_cull_times": (C.c_int, [vp, c_float_p, c_float_p]),
     "zn_scene_visible_count": (C.c_int, [vp, c_u32_p]),
     "zn_scene_read_visible": (C.c_int, [vp, vp, C.c_uint32, c_u32_p]),
     "zn_scene_read_world": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
@@ -106,6 +122,16 @@ PROTOTYPES = {
     "zn_scene_launches_per_update": (C.c_int, [vp, c_u32_p]),
     "zn_scene_set_profiling": (C.c_int, [vp, C.c_int]),
     "zn_scene_level_times": (C.c_int, [vp, vp, C.c_uint32, c_float_p]),
+    "zn_shard_scenes": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, c_u32_p, c_u32_p]),
+    "zn_scene_index_bases": (C.c_int, [vp, C.c_uint32, vp]),
+    "zn_shard_scene_by_roots": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp]),
+    "zn_exchange_create": (C.c_int, [vp, C.POINTER(ExchangeDesc), C.POINTER(vp)]),
+    "zn_exchange_destroy": (C.c_int, [vp, vp, C.c_uint32]),
+    "zn_exchange_unbind": (C.c_int, [vp, vp, C.c_uint32]),
+    "zn_exchange_bind": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64]),
+    "zn_exchange_expand": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "zn_exchange_result": (C.c_int, [vp, vp, C.POINTER(vp), c_u32_p]),
+    "zn_exchange_info": (C.c_int, [vp, c_u32_p, c_u32_p, C.POINTER(C.c_uint64)]),
     "zn_mesh_create": (C.c_int, [vp, C.POINTER(MeshDesc), C.POINTER(vp)]),
     "zn_mesh_destroy": (C.c_int, [vp]),
     "zn_mesh_set_vertices": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_size_t]),

@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libzenyth_b200.so")
-SOURCES = ["zn_ctx.cu", "zn_scene.cu", "zn_mesh.cu", "zn_synth.cu", "zn_hostmath.cpp", "zn_io.cpp", "zn_hierarchy.cpp"]
+SOURCES = ["zn_ctx.cu", "zn_scene.cu", "zn_mesh.cu", "zn_synth.cu", "zn_hostmath.cpp", "zn_io.cpp", "zn_hierarchy.cpp", "zn_exchange.cpp"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

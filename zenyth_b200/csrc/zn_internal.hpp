@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cuda.h>
@@ -64,6 +65,8 @@ struct zn_scene {
 	uint32_t index_base = 0;
 	int max_ctas = 0;              // co-resident CTAs of the persistent level kernel (4 per SM)
 	bool has_camera = false;
+	bool world_valid = false;      // an update has run: the world matrices exist (zn_scene_cull needs them)
+	bool last_update_had_view = false;
 	bool ranges_dirty = true;      // tile_prange must be rebuilt before the next update
 	float view_proj[16];
 	float planes[24];
@@ -90,7 +93,16 @@ struct zn_scene {
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
 	uint32_t* chunk_total = nullptr;       // [2][chunks] visible count per chunk, one set per frame parity
 	uint32_t frame_parity = 0;
-	uint32_t* level_ticket = nullptr;      // [levels] monotonically increasing tile tickets, one counter per level
+	uint32_t* level_ticket = nullptr;      // [levels + 2] monotonically increasing tickets: one counter per level, then the
+	                                       // cull pass's tile counter and the expansion's item counter
+	uint32_t cull_ticket_base = 0;         // tickets the cull / expansion counters have handed out in earlier launches
+	uint32_t expand_ticket_base = 0;
+	int max_ctas_cull = 0;                 // co-resident CTAs of scene_cull_kernel / expand_visible_kernel
+	int max_ctas_expand = 0;
+	CUtensorMap tm_world_all, tm_mvp_all;  // all E rows (the cull pass is one launch over every level)
+	std::vector<std::pair<void*, CUtensorMap>> mvp_maps;   // tensor maps of caller-owned MVP arrays (zn_scene_cull)
+	const void* abort_status = nullptr;    // status word of the last zn_scene_wait_flags, consumed by the next plain expansion
+	cudaEvent_t cull_events[3] = {nullptr, nullptr, nullptr};   // profiling: before cull, after cull, after emit
 	uint32_t* host_count = nullptr;      // pinned [1]
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events; // [levels+2]

@@ -57,6 +57,12 @@ __device__ __forceinline__ void tensor_store_2d(const CUtensorMap* map, const vo
 	asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
 	             ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
+// 2-D tensor-map load: global -> smem tile in the map's swizzle pattern; rows past the tensor's
+// extent arrive as zeros and still count towards the transaction bytes (always the full box).
+__device__ __forceinline__ void tensor_load_2d(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+	             ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
 	asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -17,6 +17,21 @@ static int ensure_staging(zn_ctx* ctx, size_t bytes) {
 	return ZN_OK;
 }
 
+// Function attributes are per device: set them for every scene (a process may drive several GPUs).
+static cudaError_t set_kernel_attributes() {
+	cudaError_t e;
+#define ZN_ATTR(kernel, bytes)                                                                                   \
+	if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))) != cudaSuccess) return e; \
+	if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
+	ZN_ATTR((scene_level_kernel<true, true>), kLevelSmem)
+	ZN_ATTR((scene_level_kernel<false, true>), kLevelSmem)
+	ZN_ATTR((scene_level_kernel<true, false>), kLevelSmem)
+	ZN_ATTR((scene_level_kernel<false, false>), kLevelSmem)
+	ZN_ATTR(scene_cull_kernel, kCullSmem)
+#undef ZN_ATTR
+	return cudaSuccess;
+}
+
 // Calls fn(level, lo, hi) for every level that intersects entities [first, first+count).
 template <class F>
 static int for_each_level_range(zn_scene* s, uint32_t first, uint32_t count, F&& fn) {
@@ -96,19 +111,20 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	}
 	ZN_CUDA(cudaSetDevice(ctx->device));
 	// function attributes are per device: set them for every scene (a process may drive several GPUs)
-	ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLevelSmem)));
-	ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLevelSmem)));
-	ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-	ZN_CUDA(cudaFuncSetAttribute(scene_level_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+	ZN_CUDA(set_kernel_attributes());
 	zn_scene* s = new zn_scene();
 	s->ctx = ctx;
 	s->entity_count = E;
 	// Persistent grid: as many CTAs as fit at once.
-	int per_sm_a = 0, per_sm_b = 0;
-	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, scene_level_kernel<true>, kTile, kLevelSmem));
-	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, scene_level_kernel<false>, kTile, kLevelSmem));
+	int per_sm_a = 0, per_sm_b = 0, per_sm_c = 0, per_sm_d = 0;
+	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, scene_level_kernel<true, true>, kTile, kLevelSmem));
+	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, scene_level_kernel<false, true>, kTile, kLevelSmem));
+	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, scene_cull_kernel, kTile, kCullSmem));
+	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, expand_visible_kernel, kExpandWarps * 32, 0));
 	s->max_ctas = std::min(per_sm_a, per_sm_b) * ctx->sm_count;
-	if (s->max_ctas < 1) { delete s; return fail(ZN_ERR_CUDA, "zn_scene_create: scene_level_kernel does not fit on an SM"); }
+	s->max_ctas_cull = per_sm_c * ctx->sm_count;
+	s->max_ctas_expand = per_sm_d * ctx->sm_count;
+	if (s->max_ctas < 1 || s->max_ctas_cull < 1 || s->max_ctas_expand < 1) { delete s; return fail(ZN_ERR_CUDA, "zn_scene_create: a scene kernel does not fit on an SM"); }
 	uint32_t tile_base = 0;
 	std::vector<uint32_t> tile_first;
 	for (size_t l = 0; l + 1 < offs.size(); ++l) {
@@ -134,8 +150,8 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	s->visible = s->visible_own;
 	s->visible_count = s->visible_count_own;
 	ZN_TRY(cudaMalloc(&s->chunk_total, size_t(s->chunk_count) * 2 * 4));   // two sets, by frame parity
-	ZN_TRY(cudaMalloc(&s->level_ticket, s->levels.size() * 4));
-	ZN_TRY(cudaMemsetAsync(s->level_ticket, 0, s->levels.size() * 4, ctx->stream));
+	ZN_TRY(cudaMalloc(&s->level_ticket, (s->levels.size() + 2) * 4));
+	ZN_TRY(cudaMemsetAsync(s->level_ticket, 0, (s->levels.size() + 2) * 4, ctx->stream));
 	s->record_words = record_header_words(s->chunk_count) + s->tile_count * kWarpsPerTile;
 	ZN_TRY(cudaMalloc(&s->record_own, size_t(s->record_words) * 4));
 	ZN_TRY(cudaMemsetAsync(s->record_own, 0, size_t(s->record_words) * 4, ctx->stream));
@@ -155,6 +171,11 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 		if (rc == ZN_OK) rc = encode_matrix_tensor_map(&lv.tm_mvp, s->mvp, lv.end);
 		if (rc != ZN_OK) return cleanup(rc);
 	}
+	{
+		int rc = encode_matrix_tensor_map(&s->tm_world_all, s->world, E);
+		if (rc == ZN_OK) rc = encode_matrix_tensor_map(&s->tm_mvp_all, s->mvp, E);
+		if (rc != ZN_OK) return cleanup(rc);
+	}
 	*out_scene = s;
 	return ZN_OK;
 }
@@ -169,6 +190,7 @@ int zn_scene_destroy(zn_scene* s) {
 	cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->level_ticket); cudaFree(s->record_own); cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
 	for (auto e : s->prof_events) cudaEventDestroy(e);
+	for (auto e : s->cull_events) if (e) cudaEventDestroy(e);
 	pipe_destroy(s);
 	delete s;
 	return ZN_OK;
@@ -300,11 +322,13 @@ int zn_scene_set_signal_value(zn_scene* s, uint32_t value) {
 static int expand_visible(zn_scene* s, const char* who, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
                           int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
                           const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
-                          uint32_t timeout_ms, void* status_dev) {
+                          uint32_t timeout_ms, void* status_dev, const void* abort_status) {
 	ZN_REQUIRE(s && records_dev && lists_dev && counts_dev, "%s: NULL argument", who);
 	ZN_REQUIRE(record_count >= 1 && record_count <= 64, "%s: record_count %u must be in [1, 64]", who, record_count);
 	ZN_REQUIRE(record_stride_words >= s->record_words, "%s: record stride %u < record size %u words", who, record_stride_words, s->record_words);
 	ZN_REQUIRE(list_stride >= s->entity_count, "%s: list stride %u < entity_count %u", who, list_stride, s->entity_count);
+	if (skip_index < 0 || uint32_t(skip_index) >= record_count) { skip_index = int(record_count); skip_count = 0; }   // nothing left out
+	skip_count = std::min(skip_count, record_count - uint32_t(skip_index));
 	ZN_CUDA(cudaSetDevice(s->ctx->device));
 	ExpandBases bases;
 	for (uint32_t r = 0; r < 64; ++r) bases.base[r] = (index_bases && r < record_count) ? index_bases[r] : 0u;
@@ -313,19 +337,28 @@ static int expand_visible(zn_scene* s, const char* who, const void* records_dev,
 		for (uint32_t* flag : s->peer_flags) sig.flag[sig.n++] = flag;
 		sig.value = s->signal_value;
 	}
-	expand_visible_kernel<<<dim3(s->chunk_count, record_count), 256, 0, s->ctx->stream>>>(
-		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, skip_index, int(skip_count),
-		static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),
+	// Persistent grid of autonomous warps drawing (record, chunk) items from a ticket counter: one draw
+	// per item plus one per warp (the draw that tells it to stop).
+	const uint32_t items = (record_count - skip_count) * s->chunk_count;
+	const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>((items + kExpandWarps - 1) / kExpandWarps, uint32_t(s->max_ctas_expand)));
+	uint32_t* ticket = s->level_ticket + s->levels.size() + 1;
+	expand_visible_kernel<<<grid, kExpandWarps * 32, 0, s->ctx->stream>>>(
+		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count,
+		skip_index, int(skip_count), static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),
 		static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag, uint64_t(timeout_ms) * 1000000ull,
-		static_cast<uint32_t*>(status_dev), sig);
+		static_cast<uint32_t*>(status_dev), static_cast<const uint32_t*>(abort_status), sig, ticket, s->expand_ticket_base);
+	s->expand_ticket_base += items + grid * uint32_t(kExpandWarps);
 	ZN_CUDA(cudaGetLastError());
 	return ZN_OK;
 }
 
 int zn_scene_expand_visible(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
                             const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev) {
+	ZN_REQUIRE(s, "zn_scene_expand_visible: scene is NULL");
+	const void* abort_status = s->abort_status;   // set by a zn_scene_wait_flags on this scene: a timed-out wait cancels this expansion
+	s->abort_status = nullptr;
 	return expand_visible(s, "zn_scene_expand_visible", records_dev, record_count, record_stride_words, skip_index, 1, index_bases, lists_dev,
-	                      list_stride, counts_dev, nullptr, 0, 1, 0, 0, nullptr);
+	                      list_stride, counts_dev, nullptr, 0, 1, 0, 0, nullptr, abort_status);
 }
 
 int zn_scene_expand_visible_signalled(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
@@ -336,7 +369,7 @@ int zn_scene_expand_visible_signalled(zn_scene* s, const void* records_dev, uint
 	ZN_REQUIRE(records_per_flag >= 1 && timeout_ms >= 1, "zn_scene_expand_visible_signalled: records_per_flag and timeout_ms must be >= 1");
 	ZN_REQUIRE(skip_count <= record_count, "zn_scene_expand_visible_signalled: skip_count %u > record_count %u", skip_count, record_count);
 	return expand_visible(s, "zn_scene_expand_visible_signalled", records_dev, record_count, record_stride_words, skip_index, skip_count, index_bases,
-	                      lists_dev, list_stride, counts_dev, flags_dev, flag_stride_words, records_per_flag, expected, timeout_ms, status_dev);
+	                      lists_dev, list_stride, counts_dev, flags_dev, flag_stride_words, records_per_flag, expected, timeout_ms, status_dev, nullptr);
 }
 
 int zn_scene_wait_flags(zn_scene* s, const void* flags_dev, uint32_t flag_stride_words, uint32_t flag_count, uint32_t expected,
@@ -350,6 +383,7 @@ int zn_scene_wait_flags(zn_scene* s, const void* flags_dev, uint32_t flag_stride
 	wait_flags_kernel<<<1, 64, 0, s->ctx->stream>>>(static_cast<const uint32_t*>(flags_dev), flag_stride_words, flag_count, expected,
 	                                                uint64_t(timeout_ms) * 1000000ull, static_cast<uint32_t*>(status_dev), sig);
 	ZN_CUDA(cudaGetLastError());
+	s->abort_status = status_dev;
 	return ZN_OK;
 }
 
@@ -359,9 +393,39 @@ int zn_scene_set_index_base(zn_scene* s, uint32_t index_base) {
 	return ZN_OK;
 }
 
-int zn_scene_update(zn_scene* s) {
-	ZN_REQUIRE(s, "zn_scene_update: scene is NULL");
-	if (!s->has_camera) return fail(ZN_ERR_STATE, "zn_scene_update: no camera set (call zn_scene_set_camera first)");
+namespace zn {
+
+// The emit kernel of a frame (K3): ordered visible list + record header from the masks and chunk
+// totals the level kernels (or the cull pass) left.  Launched with programmatic stream
+// serialization behind the kernel that produced them.
+static int launch_emit(zn_scene* s, const RecordTargets& rec, const uint32_t* totals, uint32_t* totals_next, uint32_t* visible,
+                       uint32_t* visible_count, uint32_t remote_tiles_below, bool pdl_ok) {
+	cudaLaunchAttribute pdl;
+	pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	pdl.val.programmaticStreamSerializationAllowed = 1;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(s->chunk_count);
+	cfg.blockDim = dim3(256);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = s->ctx->stream;
+	cfg.attrs = &pdl;
+	cfg.numAttrs = pdl_ok ? 1 : 0;
+	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, rec, (const uint32_t*)s->tile_first_entity, s->tile_count, s->chunk_count,
+	                           totals, totals_next, s->index_base, visible, visible_count, remote_tiles_below));
+	return ZN_OK;
+}
+
+static RecordTargets record_targets(const zn_scene* s) {
+	RecordTargets rec = {};
+	rec.ptr[0] = s->record;
+	rec.n = 1;
+	for (uint32_t* peer : s->peer_records) rec.ptr[rec.n++] = peer;
+	return rec;
+}
+
+// One frame on the context stream.  with_view: the fused form (world + MVP + masks, then emit);
+// otherwise TRS -> world only.
+static int run_update(zn_scene* s, bool with_view) {
 	zn_ctx* ctx = s->ctx;
 	ZN_CUDA(cudaSetDevice(ctx->device));
 	if (s->ranges_dirty) {
@@ -369,14 +433,13 @@ int zn_scene_update(zn_scene* s) {
 		ZN_CUDA(cudaGetLastError());
 		s->ranges_dirty = false;
 	}
-	FrameConst fc;
-	std::memcpy(fc.vp, s->view_proj, sizeof(fc.vp));
-	std::memcpy(fc.planes, s->planes, sizeof(fc.planes));
+	FrameConst fc = {};
+	if (with_view) {
+		std::memcpy(fc.vp, s->view_proj, sizeof(fc.vp));
+		std::memcpy(fc.planes, s->planes, sizeof(fc.planes));
+	}
 	const bool prof = s->profiling;
-	RecordTargets rec = {};
-	rec.ptr[0] = s->record;
-	rec.n = 1;
-	for (uint32_t* peer : s->peer_records) rec.ptr[rec.n++] = peer;
+	const RecordTargets rec = record_targets(s);
 	const uint32_t header_words = record_header_words(s->chunk_count);
 	// Peers get the masks of the leading run of small levels from the emit kernel, of every other
 	// level from its level kernel (see emit_chunk).
@@ -391,7 +454,7 @@ int zn_scene_update(zn_scene* s) {
 		}
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
 	uint32_t* totals_next = s->chunk_total + size_t(s->frame_parity ^ 1u) * s->chunk_count;
-	s->frame_parity ^= 1u;
+	if (with_view) s->frame_parity ^= 1u;
 	// Levels >= 1 and the emit kernel are launched with programmatic stream serialization: their
 	// prologue (and the first input-block load) overlaps the tail of the kernel before them; they
 	// call griddepcontrol.wait before touching anything that kernel wrote.  Level 0 is a normal
@@ -411,26 +474,111 @@ int zn_scene_update(zn_scene* s) {
 		cfg.numAttrs = (l == 0 || prof) ? 0 : 1;
 		if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[l], ctx->stream));
 		uint32_t* ticket = s->level_ticket + l;   // one counter per level: PDL lets consecutive levels overlap
-		if (l == 0)
-			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<false>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
-			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           l < small_levels ? rec_local : rec, header_words, totals, ticket, lv.ticket_base));
-		else
-			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_level_kernel<true>, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks,
-			                           (const uint2*)s->tile_prange, (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles,
-			                           l < small_levels ? rec_local : rec, header_words, totals, ticket, lv.ticket_base));
+		auto launch = [&](auto kernel) {
+			return cudaLaunchKernelEx(&cfg, kernel, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks, (const uint2*)s->tile_prange,
+			                          (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles, l < small_levels ? rec_local : rec,
+			                          header_words, totals, ticket, lv.ticket_base);
+		};
+		if (l == 0) ZN_CUDA(with_view ? launch(scene_level_kernel<false, true>) : launch(scene_level_kernel<false, false>));
+		else ZN_CUDA(with_view ? launch(scene_level_kernel<true, true>) : launch(scene_level_kernel<true, false>));
 		// every tile takes one ticket and every CTA one more (the draw that tells it to stop)
 		lv.ticket_base += lv.tiles + grid;
 	}
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size()], ctx->stream));
-	cfg.gridDim = dim3(s->chunk_count);
-	cfg.blockDim = dim3(256);
-	cfg.dynamicSmemBytes = 0;
-	cfg.numAttrs = prof ? 0 : 1;
-	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, rec, (const uint32_t*)s->tile_first_entity,
-	                           s->tile_count, s->chunk_count, (const uint32_t*)totals, totals_next, s->index_base, s->visible, s->visible_count,
-	                           remote_tiles_below));
+	if (with_view) {
+		const int rc = launch_emit(s, rec, totals, totals_next, s->visible, s->visible_count, remote_tiles_below, !prof);
+		if (rc != ZN_OK) return rc;
+	}
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
+	s->last_update_had_view = with_view;
+	s->world_valid = true;
+	return ZN_OK;
+}
+
+// The tensor map of a caller-owned float[E][16] MVP array (encoded once per pointer).
+static int mvp_map_for(zn_scene* s, void* mvp_dev, const CUtensorMap** out) {
+	for (auto& e : s->mvp_maps)
+		if (e.first == mvp_dev) { *out = &e.second; return ZN_OK; }
+	if (s->mvp_maps.size() >= 16) s->mvp_maps.erase(s->mvp_maps.begin());
+	CUtensorMap m;
+	const int rc = encode_matrix_tensor_map(&m, mvp_dev, s->entity_count);
+	if (rc != ZN_OK) return rc;
+	s->mvp_maps.emplace_back(mvp_dev, m);
+	*out = &s->mvp_maps.back().second;
+	return ZN_OK;
+}
+
+} // namespace zn
+
+int zn_scene_update(zn_scene* s) {
+	ZN_REQUIRE(s, "zn_scene_update: scene is NULL");
+	return run_update(s, s->has_camera);
+}
+
+int zn_scene_update_world(zn_scene* s) {
+	ZN_REQUIRE(s, "zn_scene_update_world: scene is NULL");
+	return run_update(s, false);
+}
+
+int zn_scene_clear_camera(zn_scene* s) {
+	ZN_REQUIRE(s, "zn_scene_clear_camera: scene is NULL");
+	s->has_camera = false;
+	return ZN_OK;
+}
+
+int zn_scene_cull(zn_scene* s, const float view[16], const float proj[16], const zn_cull_output* out) {
+	ZN_REQUIRE(s && view && proj, "zn_scene_cull: NULL argument");
+	if (!s->world_valid) return fail(ZN_ERR_STATE, "zn_scene_cull: no world matrices yet (call zn_scene_update or zn_scene_update_world first)");
+	zn_ctx* ctx = s->ctx;
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	uint32_t* visible = s->visible;
+	uint32_t* visible_count = s->visible_count;
+	const CUtensorMap* tm_mvp = &s->tm_mvp_all;
+	if (out) {
+		ZN_REQUIRE((out->visible_dev == nullptr) == (out->visible_count_dev == nullptr), "zn_scene_cull: pass visible_dev and visible_count_dev together");
+		if (out->visible_dev) {
+			ZN_REQUIRE(out->visible_capacity >= s->entity_count, "zn_scene_cull: visible_capacity %u < entity_count %u", out->visible_capacity, s->entity_count);
+			visible = static_cast<uint32_t*>(out->visible_dev);
+			visible_count = static_cast<uint32_t*>(out->visible_count_dev);
+		}
+		if (out->mvp_dev) {
+			ZN_REQUIRE(reinterpret_cast<uintptr_t>(out->mvp_dev) % 16 == 0, "zn_scene_cull: mvp_dev must be 16-byte aligned");
+			const int rc = mvp_map_for(s, out->mvp_dev, &tm_mvp);
+			if (rc != ZN_OK) return rc;
+		}
+	}
+	FrameConst fc;
+	float vp[16];
+	zn_mat4_mul(proj, view, vp);
+	std::memcpy(fc.vp, vp, sizeof(fc.vp));
+	zn_frustum_planes(vp, fc.planes);
+	const RecordTargets rec = record_targets(s);
+	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
+	uint32_t* totals_next = s->chunk_total + size_t(s->frame_parity ^ 1u) * s->chunk_count;
+	s->frame_parity ^= 1u;
+	const bool prof = s->profiling;
+	if (prof) ZN_CUDA(cudaEventRecord(s->cull_events[0], ctx->stream));
+	const uint32_t grid = std::min<uint32_t>(s->tile_count, uint32_t(s->max_ctas_cull));
+	uint32_t* ticket = s->level_ticket + s->levels.size();
+	scene_cull_kernel<<<grid, kTile, kCullSmem, ctx->stream>>>(s->tm_world_all, *tm_mvp, fc, s->blocks, s->tile_first_entity, s->tile_count,
+	                                                          s->entity_count, rec, record_header_words(s->chunk_count), totals, ticket,
+	                                                          s->cull_ticket_base);
+	ZN_CUDA(cudaGetLastError());
+	s->cull_ticket_base += s->tile_count + grid;
+	if (prof) ZN_CUDA(cudaEventRecord(s->cull_events[1], ctx->stream));
+	const int rc = launch_emit(s, rec, totals, totals_next, visible, visible_count, 0u, !prof);
+	if (rc != ZN_OK) return rc;
+	if (prof) ZN_CUDA(cudaEventRecord(s->cull_events[2], ctx->stream));
+	return ZN_OK;
+}
+
+int zn_scene_cull_times(zn_scene* s, float* out_cull_ms, float* out_emit_ms) {
+	ZN_REQUIRE(s && out_cull_ms, "zn_scene_cull_times: NULL argument");
+	if (!s->profiling || !s->cull_events[0]) return fail(ZN_ERR_STATE, "zn_scene_cull_times: profiling is not enabled");
+	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	ZN_CUDA(cudaEventSynchronize(s->cull_events[2]));
+	ZN_CUDA(cudaEventElapsedTime(out_cull_ms, s->cull_events[0], s->cull_events[1]));
+	if (out_emit_ms) ZN_CUDA(cudaEventElapsedTime(out_emit_ms, s->cull_events[1], s->cull_events[2]));
 	return ZN_OK;
 }
 
@@ -440,6 +588,7 @@ int zn_scene_set_profiling(zn_scene* s, int enable) {
 	if (enable && s->prof_events.empty()) {
 		s->prof_events.resize(s->levels.size() + 2);
 		for (auto& e : s->prof_events) ZN_CUDA(cudaEventCreate(&e));
+		for (auto& e : s->cull_events) ZN_CUDA(cudaEventCreate(&e));
 	}
 	s->profiling = enable != 0;
 	return ZN_OK;

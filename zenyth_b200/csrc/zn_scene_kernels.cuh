@@ -92,7 +92,10 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 	return t;
 }
 
-template <bool HAS_PARENT>
+// WITH_VIEW = false is the camera-less update (zn_scene_update_world): TRS -> world only.  It pulls
+// rows 0..8 and the parent row of a block (10 KiB instead of 16), stores the world tile and writes
+// neither MVPs nor masks; a later scene_cull_kernel pass supplies those per camera.
+template <bool HAS_PARENT, bool WITH_VIEW>
 __global__ void __launch_bounds__(kTile, 4)
 scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_constant__ CUtensorMap tm_mvp,
                    const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
@@ -126,8 +129,14 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		if (HAS_PARENT) pr = __ldg(tile_prange + gt);
 		const bool staged = HAS_PARENT && pr.y != 0u && pr.y != kGather;
 		s_meta = pr;
-		mbar_arrive_expect_tx(&s_full, kInBytes + (staged ? pr.y * 64u : 0u));
-		bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, kInBytes, &s_full);
+		if (WITH_VIEW) {
+			mbar_arrive_expect_tx(&s_full, kInBytes + (staged ? pr.y * 64u : 0u));
+			bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, kInBytes, &s_full);
+		} else {
+			mbar_arrive_expect_tx(&s_full, 10u * kTile * 4u + (staged ? pr.y * 64u : 0u));
+			bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, 9u * kTile * 4u, &s_full);
+			bulk_g2s(const_cast<uint32_t*>(in_blk) + 15 * kTile, blocks + size_t(gt) * kBlockWords + 15 * kTile, kTile * 4u, &s_full);
+		}
 		if (HAS_PARENT && first_tile) grid_dep_wait();
 		if (staged) bulk_g2s(const_cast<float4*>(in_par), world_rd + size_t(pr.x) * 16, pr.y * 64u, &s_full);
 	};
@@ -154,7 +163,7 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		mbar_wait(&s_full, n & 1u);
 		float v[15];
 #pragma unroll
-		for (int k = 0; k < 15; ++k) v[k] = __uint_as_float(in_blk[k * kTile + t]);
+		for (int k = 0; k < (WITH_VIEW ? 15 : 9); ++k) v[k] = __uint_as_float(in_blk[k * kTile + t]);
 		const uint32_t p = HAS_PARENT ? in_blk[15 * kTile + t] : ZN_NO_PARENT;
 		Affine P;
 		if (HAS_PARENT && p != ZN_NO_PARENT) {
@@ -187,9 +196,11 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		Affine w = local;
 		if (HAS_PARENT && p != ZN_NO_PARENT) w = affine_mul(P, local);
 		const uint32_t first = begin + tl * kTile;
-		const bool vis = (first + t < end) && aabb_visible(w, v[9], v[10], v[11], v[12], v[13], v[14], fc.planes);
-		const uint32_t mask = __ballot_sync(0xffffffffu, vis);
-		if (lane == 0) s_mask[warp] = mask;
+		if (WITH_VIEW) {
+			const bool vis = (first + t < end) && aabb_visible(w, v[9], v[10], v[11], v[12], v[13], v[14], fc.planes);
+			const uint32_t mask = __ballot_sync(0xffffffffu, vis);
+			if (lane == 0) s_mask[warp] = mask;
+		}
 
 		// ---- results -> swizzled shared tile (chunk c of row r lives at chunk c ^ ((r>>1)&3)) ------
 		{
@@ -199,21 +210,24 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 			wr[1 ^ sw] = make_float4(w.m[0][1], w.m[1][1], w.m[2][1], 0.0f);
 			wr[2 ^ sw] = make_float4(w.m[0][2], w.m[1][2], w.m[2][2], 0.0f);
 			wr[3 ^ sw] = make_float4(w.m[0][3], w.m[1][3], w.m[2][3], 1.0f);
-			float m[16];
-			mvp_mul(fc.vp, w, m);
-			float4* mr = out_mvp + t * 4;
-			mr[0 ^ sw] = make_float4(m[0], m[1], m[2], m[3]);
-			mr[1 ^ sw] = make_float4(m[4], m[5], m[6], m[7]);
-			mr[2 ^ sw] = make_float4(m[8], m[9], m[10], m[11]);
-			mr[3 ^ sw] = make_float4(m[12], m[13], m[14], m[15]);
+			if (WITH_VIEW) {
+				float m[16];
+				mvp_mul(fc.vp, w, m);
+				float4* mr = out_mvp + t * 4;
+				mr[0 ^ sw] = make_float4(m[0], m[1], m[2], m[3]);
+				mr[1 ^ sw] = make_float4(m[4], m[5], m[6], m[7]);
+				mr[2 ^ sw] = make_float4(m[8], m[9], m[10], m[11]);
+				mr[3 ^ sw] = make_float4(m[12], m[13], m[14], m[15]);
+			}
 		}
 		fence_proxy_async_smem();
 		__syncthreads();
 		if (t == 0) {
 			tensor_store_2d(&tm_world, out_world, 0, int32_t(first));
-			tensor_store_2d(&tm_mvp, out_mvp, 0, int32_t(first));
+			if (WITH_VIEW) tensor_store_2d(&tm_mvp, out_mvp, 0, int32_t(first));
 			bulk_commit();
 		}
+		if (!WITH_VIEW) continue;
 		if (warp == 0) {
 			const uint32_t gt = tile_base + tl;
 			const uint32_t word = (lane < kWarpsPerTile) ? s_mask[lane] : 0u;
@@ -227,6 +241,117 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 			const uint32_t word = s_mask[lane];
 			const size_t at = header_words + size_t(tile_base + tl) * kWarpsPerTile + lane;
 			for (int q = 1; q < rec.n; ++q) rec.ptr[q][at] = word;
+		}
+	}
+	if (t == 0) bulk_wait_read_all();
+}
+
+// scene_cull_kernel — a camera pass over world matrices that already exist (zn_scene_cull): what
+// Scene::Cull(camera) runs from OnRender (Core/src/Application.cpp:49-51) after OnUpdate (:47) has
+// composed the hierarchy, and again for every further view (shadow pass, second camera) without
+// redoing a sincos or rewriting a world matrix.  ONE persistent launch over all tiles of all levels
+// (the world matrices are complete, so levels no longer order anything):
+//   in   the tile's 256 world matrices — one 2-D tensor load in the 64-byte swizzle the level kernel
+//        stored them with, so the per-thread 16-byte reads are conflict-free — and rows 9..14 of its
+//        input block (AABB centre + half extent, 6 KiB, one bulk copy);
+//   out  the MVP tile (tensor store), the tile's 256-bit mask, the chunk total.
+// 152 algorithmic bytes per entity (64 + 24 in, 64 out) + the emit kernel's 4 per visible entity.
+// The tensor maps span all E rows: the last tile of a level also covers the first entities of the
+// next level, whose MVPs it computes from their real world matrices — bit for bit what the owning
+// tile stores — so the overlap is harmless; only the mask is clipped to the tile's own entities.
+constexpr uint32_t kAabbBytes = 6u * kTile * 4u;
+constexpr uint32_t kCullSmem = 2u * kTile * 64u + kAabbBytes + 1024u;
+
+__global__ void __launch_bounds__(kTile, 4)
+scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_constant__ CUtensorMap tm_mvp,
+                  const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
+                  const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t entity_count,
+                  const __grid_constant__ RecordTargets rec, uint32_t header_words, uint32_t* __restrict__ chunk_total,
+                  uint32_t* __restrict__ ticket, uint32_t ticket_base) {
+	extern __shared__ uint8_t smem_raw[];
+	__shared__ uint64_t s_full;
+	__shared__ uint2 s_meta[2];      // {first entity, entities} of the tile of iteration n (slot n&1) and n+1
+	__shared__ uint32_t s_mask[kWarpsPerTile];
+	__shared__ uint32_t s_tile[2];
+
+	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	const float4* in_world = reinterpret_cast<const float4*>(smem);
+	float4* out_mvp = reinterpret_cast<float4*>(smem + kTile * 64);
+	const float* in_aabb = reinterpret_cast<const float*>(smem + 2 * kTile * 64);
+
+	const int t = threadIdx.x;
+	const int lane = t & 31;
+	const int warp = t >> 5;
+
+	auto issue_loads = [&](uint32_t gt, uint32_t slot) {
+		const uint32_t first = __ldg(tile_first_entity + gt);
+		const uint32_t next = (gt + 1 < tiles) ? __ldg(tile_first_entity + gt + 1) : entity_count;
+		s_meta[slot] = make_uint2(first, next - first);
+		mbar_arrive_expect_tx(&s_full, kTile * 64u + kAabbBytes);
+		tensor_load_2d(const_cast<float4*>(in_world), &tm_world, 0, int32_t(first), &s_full);
+		bulk_g2s(const_cast<float*>(in_aabb), blocks + size_t(gt) * kBlockWords + 9 * kTile, kAabbBytes, &s_full);
+	};
+
+	if (t == 0) {
+		mbar_init(&s_full, 1);
+		fence_mbar_init();
+		prefetch_tensormap(&tm_world);
+		prefetch_tensormap(&tm_mvp);
+		grid_dep_launch();
+		const uint32_t g0 = atomicAdd(ticket, 1u) - ticket_base;
+		s_tile[0] = g0;
+		if (g0 < tiles) issue_loads(g0, 0);
+	}
+	__syncthreads();
+
+	for (uint32_t n = 0;; ++n) {
+		const uint32_t gt = s_tile[n & 1u];
+		if (gt >= tiles) break;
+		mbar_wait(&s_full, n & 1u);
+		const uint2 meta = s_meta[n & 1u];
+		const int sw = (t >> 1) & 3;
+		const float4 c0 = in_world[t * 4 + (0 ^ sw)], c1 = in_world[t * 4 + (1 ^ sw)], c2 = in_world[t * 4 + (2 ^ sw)],
+		             c3 = in_world[t * 4 + (3 ^ sw)];
+		float a[6];
+#pragma unroll
+		for (int k = 0; k < 6; ++k) a[k] = in_aabb[k * kTile + t];
+		if (t == 0) bulk_wait_read_all();   // tile n-1's tensor store has finished reading the out tile
+		__syncthreads();                    // input stage consumed by everyone; out tile free
+		if (t == 0) {
+			const uint32_t next = atomicAdd(ticket, 1u) - ticket_base;
+			s_tile[(n + 1u) & 1u] = next;
+			if (next < tiles) issue_loads(next, (n + 1u) & 1u);
+		}
+		Affine w;
+		w.m[0][0] = c0.x; w.m[1][0] = c0.y; w.m[2][0] = c0.z;
+		w.m[0][1] = c1.x; w.m[1][1] = c1.y; w.m[2][1] = c1.z;
+		w.m[0][2] = c2.x; w.m[1][2] = c2.y; w.m[2][2] = c2.z;
+		w.m[0][3] = c3.x; w.m[1][3] = c3.y; w.m[2][3] = c3.z;
+		const bool vis = (uint32_t(t) < meta.y) && aabb_visible(w, a[0], a[1], a[2], a[3], a[4], a[5], fc.planes);
+		const uint32_t mask = __ballot_sync(0xffffffffu, vis);
+		if (lane == 0) s_mask[warp] = mask;
+		{
+			float m[16];
+			mvp_mul(fc.vp, w, m);
+			float4* mr = out_mvp + t * 4;
+			mr[0 ^ sw] = make_float4(m[0], m[1], m[2], m[3]);
+			mr[1 ^ sw] = make_float4(m[4], m[5], m[6], m[7]);
+			mr[2 ^ sw] = make_float4(m[8], m[9], m[10], m[11]);
+			mr[3 ^ sw] = make_float4(m[12], m[13], m[14], m[15]);
+		}
+		fence_proxy_async_smem();
+		__syncthreads();
+		if (t == 0) {
+			tensor_store_2d(&tm_mvp, out_mvp, 0, int32_t(meta.x));
+			bulk_commit();
+		}
+		if (warp == 0) {
+			const uint32_t word = (lane < kWarpsPerTile) ? s_mask[lane] : 0u;
+			const size_t at = header_words + size_t(gt) * kWarpsPerTile + lane;
+			if (lane < kWarpsPerTile)
+				for (int q = 0; q < rec.n; ++q) rec.ptr[q][at] = word;
+			const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(word));
+			if (lane == 0) atomicAdd(chunk_total + gt / kChunkTiles, cnt);
 		}
 	}
 	if (t == 0) bulk_wait_read_all();
@@ -426,7 +551,9 @@ emit_visible_kernel(const __grid_constant__ RecordTargets rec, const uint32_t* _
 }
 
 // Signal + wait as a kernel of their own (one thread per flag), for comparison with the form fused
-// into expand_visible_kernel: the kernel boundary orders the expansion after it.
+// into expand_visible_kernel: the kernel boundary orders the expansion after it.  A flag that does
+// not arrive within the timeout stores 1 + its index into *status; an expansion launched with that
+// status word (zn_scene_expand_visible after zn_scene_wait_flags) then expands nothing.
 __global__ void wait_flags_kernel(const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t count, uint32_t expected,
                                   uint64_t timeout_ns, uint32_t* __restrict__ status, const __grid_constant__ SignalTargets sig) {
 	const uint32_t r = threadIdx.x;
@@ -435,95 +562,149 @@ __global__ void wait_flags_kernel(const uint32_t* __restrict__ flags, uint32_t f
 	const uint64_t t0 = global_timer_ns();
 	while (int32_t(ld_acquire_sys(flags + size_t(r) * flag_stride) - expected) < 0) {
 		if (global_timer_ns() - t0 > timeout_ns) {
-			atomicExch(status, 1u + r);
+			atomicCAS(status, 0u, 1u + r);
 			break;
 		}
 		__nanosleep(200);
 	}
 }
 
-// Expands `gridDim.y` visibility records (this rank's and its peers', as all-gathered) into their
-// ordered index lists: lists[r*list_stride ...], counts[r].  Same arithmetic as emit_visible_kernel,
-// so every rank derives bit-identical lists from the 27x smaller records.
+// Expands visibility records (this rank's and its peers', as all-gathered) into their ordered
+// index lists: lists[r*list_stride ...], counts[r].  Same arithmetic as emit_visible_kernel, so
+// every rank derives bit-identical lists from the 27x smaller records.
 struct ExpandBases {
 	uint32_t base[64];
 };
-// A record already carries every offset the owner computed (chunk bases, group offsets), so a warp
-// here is autonomous: 32 mask words (4 tiles) + two offsets in, a warp scan, the scatter out — no
-// shared-memory reduction, no block barrier.
-__global__ void __launch_bounds__(256)
+constexpr int kExpandWarps = 8;   // warps per CTA of the persistent expansion grid
+
+// A record already carries every offset its owner computed (chunk bases, group offsets), so a WARP
+// is autonomous: it draws one (record, chunk) item at a time from a ticket counter, reads the
+// chunk's ten header words, and then
+//   - skips an empty chunk or 4-tile group,
+//   - writes a full group as one run of 1024 consecutive indices,
+//   - walks the masks only of mixed groups (all 256 mask words of a mixed chunk are fetched with
+//     one round of coalesced loads before the first group is scattered).
+// The grid is persistent (as many CTAs as fit, no CTA is spent on an empty chunk) and no block
+// barrier or shared-memory reduction is involved.
+//
+// Signalled form (flags != nullptr): a warp waits — lane 0, ld.acquire.sys, bounded — for the flag
+// of a record's owner the first time it draws an item of that record.  If the flag does not arrive
+// within the timeout the record is NOT expanded: 1 + r goes to *status (first failure wins),
+// counts[r] becomes 0 and every later item of that record is dropped, so a half-written record
+// never reaches the scatter.  `abort_status` (plain form after zn_scene_wait_flags): a non-zero word
+// there means that wait failed; nothing is expanded and all counts are zeroed.
+__global__ void __launch_bounds__(kExpandWarps * 32)
 expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
-                      uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, int skip, int skip_count,
+                      uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, uint32_t record_count, int skip, int skip_count,
                       uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ counts,
                       const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t expected, uint32_t records_per_flag,
-                      uint64_t timeout_ns, uint32_t* __restrict__ status, const __grid_constant__ SignalTargets sig) {
-	__shared__ __align__(16) uint32_t s_word[256];
-	__shared__ __align__(16) uint32_t s_off[256];
-	__shared__ uint32_t s_first[kChunkTiles];
-	const uint32_t r = blockIdx.y;
-	if (sig.n > 0 && blockIdx.x == 0 && r == 0 && threadIdx.x == 0) {
+                      uint64_t timeout_ns, uint32_t* __restrict__ status, const uint32_t* __restrict__ abort_status,
+                      const __grid_constant__ SignalTargets sig, uint32_t* __restrict__ ticket, uint32_t ticket_base) {
+	__shared__ __align__(16) uint32_t s_word[kExpandWarps][32];
+	__shared__ __align__(16) uint32_t s_off[kExpandWarps][32];
+	__shared__ uint32_t s_first[kExpandWarps][4];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (sig.n > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
 		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank
 		raise_flags(sig);
 	}
-	if (int(r) >= skip && int(r) < skip + skip_count) return;   // records whose lists the caller already has (its own scenes')
-	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	if (flags) {
-		// Record r was stored into this GPU's memory by its owner's kernels (SignalTargets above): wait
-		// for the owner's flag to reach this frame's sequence number.  Sequence numbers wrap, hence the
-		// signed distance.  The wait is bounded: a peer that never signals sets *status instead of
-		// hanging the GPU.
-		if (t == 0) {
-			const uint32_t* f = flags + size_t(r / records_per_flag) * flag_stride;
-			const uint64_t t0 = global_timer_ns();
-			while (int32_t(ld_acquire_sys(f) - expected) < 0) {
-				if (global_timer_ns() - t0 > timeout_ns) {
-					atomicExch(status, 1u + r);
-					break;
-				}
-				__nanosleep(200);
-			}
-		}
-		__syncthreads();
-	}
-	const uint32_t* rec = records + size_t(r) * record_stride;
-	const uint32_t* masks = rec + record_header_words(chunks);
-	uint32_t* visible = lists + size_t(r) * list_stride;
-	const uint32_t chunk = blockIdx.x;
-	if (chunk == 0 && t == 0) counts[r] = __ldcg(rec + chunks);
-	// The header already holds every count: entry chunk+1 is the next chunk's base (or, after the
-	// last chunk, the total), and a group's count is the distance to the next group's offset.  An
-	// empty chunk or group is skipped, a full group is one run of 1024 indices — in both cases
-	// without reading a mask word.
-	const uint32_t chunk_base = __ldcg(rec + chunk);
-	const uint32_t chunk_count = __ldcg(rec + chunk + 1u) - chunk_base;
-	if (chunk_count == 0u) return;                            // CTA-uniform
-	const uint32_t group = chunk * 8u + warp;                 // 4 tiles = 32 mask words
-	const uint32_t tile = group * 4u + (lane >> 3);
-	if (group * 4u >= tiles) return;                          // whole group past the end (warp-uniform)
-	const uint32_t group_off = __ldcg(rec + chunks + 1u + group);
-	const uint32_t group_count = (warp < 7 ? __ldcg(rec + chunks + 2u + group) : chunk_count) - group_off;
-	if (group_count == 0u) return;                            // warp-uniform
-	const uint32_t base = chunk_base + group_off;
-	if (group_count == 4u * kTile) {
-		store_run_1024(visible + base, tile_first_entity[group * 4u] + bases.base[r], lane);
+	const uint32_t live = record_count - uint32_t(skip_count);       // records this launch expands
+	const uint32_t items = live * chunks;
+	if (abort_status && __ldcg(abort_status) != 0u) {
+		if (blockIdx.x == 0 && threadIdx.x < record_count && !(int(threadIdx.x) >= skip && int(threadIdx.x) < skip + skip_count)) counts[threadIdx.x] = 0u;
+		// keep the ticket counter where the host expects it after this launch (every item + one stop draw per warp)
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(ticket, items + gridDim.x * uint32_t(kExpandWarps));
 		return;
 	}
-	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
-	const uint32_t cnt = __popc(word);
-	uint32_t incl = cnt;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-		if (lane >= d) incl += y;
-	}
-	s_word[t] = word;
-	s_off[t] = base + incl - cnt;
-	if ((lane & 7) == 0) s_first[t >> 3] = (tile < tiles) ? tile_first_entity[tile] + bases.base[r] : 0u;
-	__syncwarp();
 	const uint32_t lt = (1u << lane) - 1u;
-	const uint4* w4 = reinterpret_cast<const uint4*>(s_word + warp * 32);
-	const uint4* o4 = reinterpret_cast<const uint4*>(s_off + warp * 32);
-	scatter_warp_words(w4, o4, s_first + warp * 4, lane, lt, visible);
+	uint64_t ready = 0, failed = 0;                                  // per-warp memo of the records' flags (warp-uniform)
+	for (;;) {
+		uint32_t item = 0;
+		if (lane == 0) item = atomicAdd(ticket, 1u) - ticket_base;
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if (item >= items) break;
+		// chunk-major: consecutive tickets belong to different records, so warps that must wait for one
+		// owner's flag leave the other records' chunks to the rest of the grid
+		const uint32_t chunk = item / live;
+		uint32_t r = item - chunk * live;
+		if (int(r) >= skip) r += uint32_t(skip_count);
+		if (flags && !((ready >> r) & 1ull)) {
+			if ((failed >> r) & 1ull) {
+				if (chunk == 0 && lane == 0) counts[r] = 0u;
+				continue;
+			}
+			uint32_t ok = 1u;
+			if (lane == 0) {
+				const uint32_t* f = flags + size_t(r / records_per_flag) * flag_stride;
+				const uint64_t t0 = global_timer_ns();
+				while (int32_t(ld_acquire_sys(f) - expected) < 0) {
+					// someone else already gave up on this record, or the time is up
+					if (*reinterpret_cast<volatile uint32_t*>(status) == 1u + r || global_timer_ns() - t0 > timeout_ns) {
+						atomicCAS(status, 0u, 1u + r);
+						ok = 0u;
+						break;
+					}
+					__nanosleep(200);
+				}
+			}
+			ok = __shfl_sync(0xffffffffu, ok, 0);     // also extends lane 0's acquire to the warp
+			if (!ok) {
+				failed |= 1ull << r;
+				if (chunk == 0 && lane == 0) counts[r] = 0u;
+				continue;
+			}
+			ready |= 1ull << r;
+		}
+		const uint32_t* rec = records + size_t(r) * record_stride;
+		const uint32_t* masks = rec + record_header_words(chunks);
+		uint32_t* visible = lists + size_t(r) * list_stride;
+		// header: lane 0 the chunk's base, lane 1 the next chunk's (or the total), lanes 8..15 the group offsets
+		uint32_t h = 0;
+		if (lane < 2) h = __ldcg(rec + chunk + lane);
+		else if (lane >= 8 && lane < 16) h = __ldcg(rec + chunks + 1u + chunk * 8u + (lane - 8));
+		const uint32_t chunk_base = __shfl_sync(0xffffffffu, h, 0);
+		const uint32_t chunk_count = __shfl_sync(0xffffffffu, h, 1) - chunk_base;
+		if (chunk == 0 && lane == 0) counts[r] = __ldcg(rec + chunks);
+		if (chunk_count == 0u || chunk_count > uint32_t(kChunkTiles * kTile)) continue;   // empty (or not a record)
+		const bool mixed_chunk = chunk_count != uint32_t(kChunkTiles * kTile);
+		uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+		if (mixed_chunk) {
+#pragma unroll
+			for (int g = 0; g < 8; ++g) {
+				const uint32_t tile = (chunk * 8u + g) * 4u + (lane >> 3);
+				w[g] = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
+			}
+		}
+#pragma unroll
+		for (int g = 0; g < 8; ++g) {
+			const uint32_t group = chunk * 8u + g;
+			if (group * 4u >= tiles) break;
+			const uint32_t group_off = __shfl_sync(0xffffffffu, h, 8 + g);
+			const uint32_t group_end = (g < 7) ? __shfl_sync(0xffffffffu, h, 9 + g) : chunk_count;
+			const uint32_t group_count = group_end - group_off;
+			if (group_count == 0u || group_count > 4u * kTile) continue;
+			const uint32_t base = chunk_base + group_off;
+			if (group_count == 4u * kTile) {
+				store_run_1024(visible + base, __ldg(tile_first_entity + group * 4u) + bases.base[r], lane);
+				continue;
+			}
+			const uint32_t tile = group * 4u + (lane >> 3);
+			const uint32_t word = w[g];
+			const uint32_t cnt = __popc(word);
+			uint32_t incl = cnt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+				if (lane >= d) incl += y;
+			}
+			__syncwarp();
+			s_word[warp][lane] = word;
+			s_off[warp][lane] = base + incl - cnt;
+			if ((lane & 7) == 0) s_first[warp][lane >> 3] = (tile < tiles) ? __ldg(tile_first_entity + tile) + bases.base[r] : 0u;
+			__syncwarp();
+			scatter_warp_words(reinterpret_cast<const uint4*>(s_word[warp]), reinterpret_cast<const uint4*>(s_off[warp]), s_first[warp], lane, lt, visible);
+		}
+	}
 }
 
 // Visible list -> what a draw submission consumes: the MVP matrices of the

@@ -277,7 +277,9 @@ class Scene:
                                                 _p(bases), C.c_void_p(lists_ptr), list_stride, C.c_void_p(counts_ptr)))
 
     def BindPeerSignal(self, flag_ptrs) -> None:
-        """Every update ends by raising these flag words (one per rank, mapped peer memory) to the signal value."""
+        """The flag words (one per rank, mapped peer memory) that the NEXT ExpandVisibleSignalled / WaitFlags launch
+        raises to the signal value — the update itself raises nothing (zenyth_b200.h), so the last frame of a run
+        must be followed by one more such call."""
         flag_ptrs = list(flag_ptrs)
         arr = (C.c_void_p * max(len(flag_ptrs), 1))(*flag_ptrs)
         check(self._lib.zn_scene_bind_peer_signal(self._h, arr, len(flag_ptrs)))
@@ -324,8 +326,30 @@ class Scene:
 
     # -- frame --------------------------------------------------------------------------------
     def Update(self) -> None:
-        """One frame, asynchronous: world, MVP, visible list (zn_scene_update)."""
+        """One frame, asynchronous: world, MVP, visible list (zn_scene_update).  Without a camera: world only."""
         check(self._lib.zn_scene_update(self._h))
+
+    def UpdateWorld(self) -> None:
+        """TRS -> world over the hierarchy only (zn_scene_update_world): what OnUpdate(dt) calls."""
+        check(self._lib.zn_scene_update_world(self._h))
+
+    def Cull(self, camera: "Camera", mvp_ptr: int | None = None, visible_ptr: int | None = None, capacity: int = 0,
+             count_ptr: int | None = None) -> None:
+        """One camera pass over the existing world matrices (zn_scene_cull): MVP, cull, ordered list.
+        Optional raw device pointers redirect this pass's results; default: the scene's own buffers."""
+        out = None
+        if mvp_ptr or visible_ptr or count_ptr:
+            out = C.byref(_capi.CullOutput(C.c_void_p(mvp_ptr or 0), C.c_void_p(visible_ptr or 0), capacity, C.c_void_p(count_ptr or 0)))
+        check(self._lib.zn_scene_cull(self._h, _p(camera.view), _p(camera.proj), out))
+
+    def ClearCamera(self) -> None:
+        check(self._lib.zn_scene_clear_camera(self._h))
+
+    def CullTimesMs(self):
+        """(cull kernel ms, emit kernel ms) of the last Cull; needs SetProfiling(True)."""
+        a, b = C.c_float(), C.c_float()
+        check(self._lib.zn_scene_cull_times(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def FrameHost(self, position=None, rotation=None, scale=None, world=None, mvp=None, visible=None) -> int:
         """End-to-end frame with host buffers (zn_scene_frame_host). Returns the visible count."""
