@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ZN_ABI_VERSION 1
+#define ZN_ABI_VERSION 2
 
 #define ZN_OK 0
 #define ZN_ERR_INVALID 1   /* bad argument */
@@ -70,6 +70,11 @@ int zn_host_free(zn_ctx* ctx, void* ptr);
  * MPI, a pipe). */
 int zn_device_alloc(zn_ctx* ctx, size_t bytes, void** out_ptr);
 int zn_device_free(zn_ctx* ctx, void* ptr);
+/* Synchronising copies between host memory and any device pointer this library handed out or was
+ * given (lists of an exchange, draw arguments, caller-owned cull outputs): for hosts that do not
+ * link the CUDA runtime themselves. */
+int zn_device_read(zn_ctx* ctx, const void* dev_ptr, void* host_dst, size_t bytes);
+int zn_device_write(zn_ctx* ctx, void* dev_ptr, const void* host_src, size_t bytes);
 int zn_ipc_export(zn_ctx* ctx, void* dev_ptr, unsigned char out_handle[64]);
 int zn_ipc_open(zn_ctx* ctx, const unsigned char handle[64], void** out_dev_ptr);
 int zn_ipc_close(zn_ctx* ctx, void* dev_ptr);
@@ -248,27 +253,32 @@ int zn_scene_device_buffers(zn_scene* scene, zn_scene_buffers* out);
 int zn_scene_build_draw(zn_scene* scene, uint32_t index_count_per_instance, void* instance_mvp_dev, uint32_t instance_capacity,
                         void* draw_args_dev);
 
-/* End-to-end frame with HOST buffers: uploads the packed [E][3] inputs (NULL = keep what is
- * resident), runs the frame, downloads what is asked for (NULL = leave on the device), and
- * returns after the data has landed.  This is the call a CPU engine would swap in. */
+/* End-to-end frame with HOST buffers: uploads the packed [count][3] inputs that are not NULL for the
+ * entity range [first, first+count) (NULL = keep what is resident; count == 0 = the whole scene),
+ * runs the frame, downloads what is asked for (NULL = leave on the device), and returns after the
+ * data has landed.  This is the call a CPU engine would swap in.  A frame that only spins its
+ * entities passes `rotation` alone (12 bytes per entity instead of 36). */
 typedef struct zn_frame_host_io {
-	const float* position;      /* in  [E][3] or NULL */
-	const float* rotation;      /* in  [E][3] or NULL */
-	const float* scale;         /* in  [E][3] or NULL */
+	const float* position;      /* in  [count][3] or NULL */
+	const float* rotation;      /* in  [count][3] or NULL */
+	const float* scale;         /* in  [count][3] or NULL */
 	float* world;               /* out [E][16] or NULL */
 	float* mvp;                 /* out [E][16] or NULL */
 	uint32_t* visible;          /* out [E] or NULL */
 	uint32_t visible_count;     /* out */
+	uint32_t first;             /* in  first entity the input arrays cover */
+	uint32_t count;             /* in  entities they cover; 0 = entity_count - first */
 } zn_frame_host_io;
 int zn_scene_frame_host(zn_scene* scene, zn_frame_host_io* io);
 /* The same frame, pipelined: up to two frames in flight.  submit() enqueues the upload of the
- * packed position/rotation/scale arrays (all three required, page-locked memory for overlap), the
- * update and the download of the visible count, and returns; wait() completes the OLDEST submitted
- * frame: fills io->visible_count and, when io->visible is not NULL, io->visible[0..count).  The
- * upload of frame k+1 overlaps the update and the download of frame k (PCIe is full duplex), so a
- * steady-state frame costs max(upload, update, download) instead of their sum.  The host arrays
- * passed to submit() must stay untouched until the matching wait() returns; world/mvp of
- * zn_frame_host_io are ignored here (they stay on the device: zn_scene_device_buffers). */
+ * non-NULL input arrays (page-locked memory for overlap), ONE repack launch into the tile-major
+ * blocks, the update and the download of the visible count, and returns; wait() completes the
+ * OLDEST submitted frame: fills io->visible_count and, when io->visible is not NULL,
+ * io->visible[0..count).  The upload of frame k+1 overlaps the update and the download of frame k
+ * (PCIe is full duplex), so a steady-state frame costs max(upload, update, download) instead of
+ * their sum.  The host arrays passed to submit() must stay untouched until the matching wait()
+ * returns; world/mvp of zn_frame_host_io are ignored here (they stay on the device:
+ * zn_scene_device_buffers). */
 int zn_scene_frame_host_submit(zn_scene* scene, const zn_frame_host_io* io);
 int zn_scene_frame_host_wait(zn_scene* scene, zn_frame_host_io* io);
 
@@ -283,6 +293,11 @@ int zn_scene_launches_per_update(zn_scene* scene, uint32_t* out_launches);
  * of the scan+emit tail (out_tail_ms, may be NULL).  Synchronises. */
 int zn_scene_set_profiling(zn_scene* scene, int enable);
 int zn_scene_level_times(zn_scene* scene, float* out_ms, uint32_t capacity, float* out_tail_ms);
+/* Test support: the persistent kernels claim their tiles from monotonically increasing 32-bit ticket
+ * counters (one per level, one for the cull pass, one for the expansion) that wrap after ~2^32
+ * tickets — every ~74k frames for the last level of the 16M scene.  This call restarts all of them
+ * at `origin` (e.g. 0xFFFFFF00) so a test can run a scene across the wrap.  Synchronises. */
+int zn_scene_set_ticket_origin(zn_scene* scene, uint32_t origin);
 /* With profiling enabled: device time of the LAST zn_scene_cull's cull kernel and of its emit kernel. */
 int zn_scene_cull_times(zn_scene* scene, float* out_cull_ms, float* out_emit_ms);
 

@@ -114,6 +114,9 @@ public:
 
 	void SetStream(void* cudaStream) { detail::Check(zn_ctx_set_stream(m_ctx, cudaStream), "GpuContext::SetStream"); }
 	void Sync() { detail::Check(zn_ctx_sync(m_ctx), "GpuContext::Sync"); }
+	// Synchronising device <-> host copies for hosts that do not link the CUDA runtime themselves.
+	void Read(const void* device, void* host, size_t bytes) { detail::Check(zn_device_read(m_ctx, device, host, bytes), "GpuContext::Read"); }
+	void Write(void* device, const void* host, size_t bytes) { detail::Check(zn_device_write(m_ctx, device, host, bytes), "GpuContext::Write"); }
 	[[nodiscard]] zn_ctx* Handle() const noexcept { return m_ctx; }
 
 private:
@@ -223,18 +226,19 @@ public:
 	// The all-in-one frame a CPU engine swaps in: uploads the packed host arrays that are not null,
 	// updates, downloads what is asked for; returns the visible count after the data has landed.
 	uint32_t FrameHost(const float* position, const float* rotation, const float* scale, float* world, float* mvp, uint32_t* visible) {
-		zn_frame_host_io io{position, rotation, scale, world, mvp, visible, 0};
+		zn_frame_host_io io{position, rotation, scale, world, mvp, visible, 0, 0, 0};
 		detail::Check(zn_scene_frame_host(m_scene, &io), "Scene::FrameHost");
 		return io.visible_count;
 	}
 	// The same frame pipelined, up to two in flight: the upload of frame k+1 overlaps the update and
 	// the download of frame k.  The arrays must stay untouched until the matching WaitFrameHost.
-	void SubmitFrameHost(const float* position, const float* rotation, const float* scale) {
-		const zn_frame_host_io io{position, rotation, scale, nullptr, nullptr, nullptr, 0};
+	// Arrays that are null are not uploaded; the others cover entities [first, first+count) (count 0: to the end).
+	void SubmitFrameHost(const float* position, const float* rotation, const float* scale, uint32_t first = 0, uint32_t count = 0) {
+		const zn_frame_host_io io{position, rotation, scale, nullptr, nullptr, nullptr, 0, first, count};
 		detail::Check(zn_scene_frame_host_submit(m_scene, &io), "Scene::SubmitFrameHost");
 	}
 	uint32_t WaitFrameHost(uint32_t* visible) {
-		zn_frame_host_io io{nullptr, nullptr, nullptr, nullptr, nullptr, visible, 0};
+		zn_frame_host_io io{nullptr, nullptr, nullptr, nullptr, nullptr, visible, 0, 0, 0};
 		detail::Check(zn_scene_frame_host_wait(m_scene, &io), "Scene::WaitFrameHost");
 		return io.visible_count;
 	}
@@ -339,6 +343,126 @@ private:
 	uint32_t m_vertexCount = 0;
 };
 
+// ---- multi-GPU host layer (one process per GPU) -----------------------------------
+// Independent scenes over ranks: the scene ids rank `rank` owns (contiguous blocks, sizes differing
+// by at most one) and every scene's global index base (-> Scene::SetIndexBase).
+[[nodiscard]] inline std::vector<uint32_t> ShardScenes(uint32_t sceneCount, uint32_t worldSize, uint32_t rank) {
+	uint32_t first = 0, count = 0;
+	detail::Check(zn_shard_scenes(sceneCount, worldSize, rank, &first, &count), "ShardScenes");
+	std::vector<uint32_t> ids(count);
+	for (uint32_t k = 0; k < count; ++k) ids[k] = first + k;
+	return ids;
+}
+[[nodiscard]] inline std::vector<uint32_t> SceneIndexBases(const std::vector<uint32_t>& entityCounts) {
+	std::vector<uint32_t> bases(entityCounts.size());
+	detail::Check(zn_scene_index_bases(entityCounts.data(), static_cast<uint32_t>(entityCounts.size()), bases.data()), "SceneIndexBases");
+	return bases;
+}
+
+// ONE scene split into hierarchy-closed entity shards by root subtree.  A shard is a scene of its
+// own: levelOffsets / parent (shard-local indices) are what SceneDesc and Scene::SetParents take,
+// globalIndex[local] maps a shard-local visible index back to the scene (monotonic, so a shard's
+// ascending list stays ascending).  Per-entity arrays follow globalIndex.
+struct SceneShard {
+	std::vector<uint32_t> globalIndex;    // [n] ascending
+	std::vector<uint32_t> parent;         // [n] shard-local, ZN_NO_PARENT for roots
+	std::vector<uint32_t> levelOffsets;   // [levels + 1]; levels the shard owns nothing of are dropped
+};
+[[nodiscard]] inline std::vector<SceneShard> ShardSceneByRoots(const std::vector<uint32_t>& levelOffsets, const std::vector<uint32_t>& parent,
+                                                               uint32_t worldSize) {
+	if (levelOffsets.size() < 2) throw std::runtime_error("ShardSceneByRoots : levelOffsets needs at least one level");
+	const uint32_t levels = static_cast<uint32_t>(levelOffsets.size() - 1), E = levelOffsets.back();
+	if (!parent.empty() && parent.size() != E) throw std::runtime_error("ShardSceneByRoots : parent must be empty or hold one entry per entity");
+	std::vector<uint32_t> owner(E), local(E), counts(worldSize);
+	detail::Check(zn_shard_scene_by_roots(levelOffsets.data(), levels, parent.empty() ? nullptr : parent.data(), worldSize, owner.data(), local.data(),
+	                                      counts.data()), "ShardSceneByRoots");
+	std::vector<SceneShard> shards(worldSize);
+	std::vector<std::vector<uint32_t>> perLevel(worldSize, std::vector<uint32_t>(levels, 0u));
+	for (uint32_t r = 0; r < worldSize; ++r) { shards[r].globalIndex.reserve(counts[r]); shards[r].parent.reserve(counts[r]); }
+	for (uint32_t l = 0; l < levels; ++l)
+		for (uint32_t e = levelOffsets[l]; e < levelOffsets[l + 1]; ++e) {
+			SceneShard& s = shards[owner[e]];
+			s.globalIndex.push_back(e);
+			const uint32_t p = parent.empty() ? ZN_NO_PARENT : parent[e];
+			s.parent.push_back(p == ZN_NO_PARENT ? ZN_NO_PARENT : local[p]);
+			perLevel[owner[e]][l]++;
+		}
+	for (uint32_t r = 0; r < worldSize; ++r) {
+		shards[r].levelOffsets.push_back(0u);
+		for (uint32_t l = 0; l < levels; ++l)
+			if (perLevel[r][l]) shards[r].levelOffsets.push_back(shards[r].levelOffsets.back() + perLevel[r][l]);
+	}
+	return shards;
+}
+
+// The per-frame exchange of compacted visible lists, fused into the compute kernels over NVLink
+// peer memory (zn_exchange_*): every rank ends up with every rank's list and count; no collective
+// library is involved.  The caller supplies one blocking HOST all-gather (MPI_Allgather, a socket,
+// ...) used at construction and destruction only — both are therefore collective.
+//     per frame k:  exchange.Bind(scenes, k);  scene.Update() for every owned scene;  exchange.Expand(k - 1);
+//     at the end:   exchange.Expand(last);  auto lists = exchange.Result();
+struct PeerExchangeDesc {
+	uint32_t worldSize = 1;
+	uint32_t rank = 0;
+	uint32_t recordsPerRank = 1;          // scenes this rank owns (the same on every rank)
+	uint32_t timeoutMs = 2000;
+	zn_allgather_fn allGather = nullptr;  // int(void* user, const void* send, void* recv, size_t bytes)
+	void* user = nullptr;
+	std::vector<uint32_t> indexBases;     // [worldSize * recordsPerRank] added to each record's indices; empty = none
+};
+class PeerExchange {
+public:
+	struct Lists {
+		std::vector<uint32_t> counts;     // [worldSize * recordsPerRank]
+		const uint32_t* device = nullptr; // list r is device[r * stride .. r * stride + counts[r])
+		uint32_t stride = 0;
+	};
+	// `layout`: any scene with the level layout all exchanged scenes share (sizes the records and lists).
+	PeerExchange(GpuContext& ctx, Scene& layout, const PeerExchangeDesc& desc) : m_indexBases(desc.indexBases) {
+		const zn_scene_buffers b = layout.DeviceBuffers();
+		zn_exchange_desc d{};
+		d.world_size = desc.worldSize; d.rank = desc.rank; d.records_per_rank = desc.recordsPerRank;
+		d.record_words = b.visibility_record_words; d.list_capacity = b.entity_count;
+		d.slots = 0; d.timeout_ms = desc.timeoutMs; d.allgather = desc.allGather; d.user = desc.user;
+		detail::Check(zn_exchange_create(ctx.Handle(), &d, &m_exchange), "PeerExchange::PeerExchange");
+		m_total = desc.worldSize * desc.recordsPerRank;
+		if (!m_indexBases.empty() && m_indexBases.size() != m_total) {
+			zn_exchange_destroy(m_exchange, nullptr, 0);
+			throw std::runtime_error("PeerExchange::PeerExchange : indexBases must hold one entry per record");
+		}
+	}
+	~PeerExchange() { if (m_exchange) zn_exchange_destroy(m_exchange, m_bound.data(), static_cast<uint32_t>(m_bound.size())); }
+	PeerExchange(const PeerExchange&) = delete;
+	PeerExchange& operator=(const PeerExchange&) = delete;
+
+	void Bind(const std::vector<Scene*>& scenes, uint64_t frame) {
+		m_bound.clear();
+		for (Scene* s : scenes) m_bound.push_back(s->Handle());
+		detail::Check(zn_exchange_bind(m_exchange, m_bound.data(), static_cast<uint32_t>(m_bound.size()), frame), "PeerExchange::Bind");
+	}
+	// Derive every PEER's list of `frame` (asynchronous; waits on the device for the owners' flags).
+	void Expand(int64_t frame) {
+		if (m_bound.empty()) throw std::runtime_error("PeerExchange::Expand : Bind first");
+		detail::Check(zn_exchange_expand(m_exchange, m_bound[0], frame, m_indexBases.empty() ? nullptr : m_indexBases.data()), "PeerExchange::Expand");
+	}
+	// Counts and device lists of the last expanded frame (synchronises); throws if a peer never signalled.
+	[[nodiscard]] Lists Result() {
+		Lists out;
+		out.counts.resize(m_total);
+		void* dev = nullptr;
+		detail::Check(zn_exchange_result(m_exchange, out.counts.data(), &dev, &out.stride), "PeerExchange::Result");
+		out.device = static_cast<const uint32_t*>(dev);
+		return out;
+	}
+	[[nodiscard]] zn_exchange* Handle() const noexcept { return m_exchange; }
+
+private:
+	zn_exchange* m_exchange = nullptr;
+	uint32_t m_total = 0;
+	std::vector<uint32_t> m_indexBases;
+	std::vector<zn_scene*> m_bound;
+};
+
 // The reference's plugin seam, in its four-method shape (Core/include/IRenderer.hpp:5-12), with a
 // portable handle in place of HWND.  A D3D12 (or any) renderer owns one of these beside its swap
 // chain: BeginFrame runs the scene update the draw depends on, EndFrame leaves world / MVP /
@@ -351,6 +475,9 @@ public:
 		m_scene.SetCamera(m_camera);
 		m_scene.Update();
 	}
+	// A second view of the same frame (shadow pass, a camera that moved after OnUpdate): re-cull
+	// without recomposing the hierarchy.
+	void CullView(const Camera& camera) { m_scene.Cull(camera); }
 	void EndFrame() { m_visibleCount = m_scene.VisibleCount(); }
 	void Resize(uint32_t width, uint32_t height) { m_camera.Resize(width, height); }
 	[[nodiscard]] uint32_t VisibleCount() const noexcept { return m_visibleCount; }

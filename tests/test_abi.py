@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(zn_lib):
     for name in names:
         assert hasattr(zn_lib, name), f"{name} is declared in include/zenyth_b200.h but not exported"
     assert sorted(_capi.PROTOTYPES) == names, "zenyth_b200/_capi.py PROTOTYPES and the header disagree"
-    assert zn_lib.zn_abi_version() == 1
+    assert zn_lib.zn_abi_version() == 2
 
 
 def test_library_is_self_contained(zn_lib):

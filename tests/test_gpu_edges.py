@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import same_values
-from oracle.binding import BASE_SEED, camera
+from oracle.binding import BASE_SEED, camera, h8_geo_level_sizes
 
 pytestmark = pytest.mark.gpu
 
@@ -156,4 +156,39 @@ def test_many_frames_no_races(oracle, gpu_ctx):
     # counts of unchecked frames: recompute a sample on the CPU
     for f in (3, 77, 151, 299):
         assert counts[f] == oracle.scene_update(arrays, views[f], proj, threads=oracle.hardware_threads(), want_mvp=False)["visible"].size, f
+    sc.Close()
+
+
+def test_tile_tickets_wrap_around_2_to_the_32(oracle, gpu_ctx):
+    """The persistent kernels' ticket counters are 32-bit and only ever grow (level 7 of the 16M scene
+    wraps every ~74k frames).  Start them just below 2^32 and run across the wrap: update, cull and the
+    record expansion must keep producing the oracle's results on every frame."""
+    import torch
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 5)                    # 4,681 entities: 40 tiles, ~100 tickets per frame and level
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    E = sum(sizes)
+    view, proj = camera(oracle)
+    ref = oracle.scene_update(arrays, view, proj)
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.Load(arrays)
+    cam = zn.Camera(view=view, proj=proj)
+    sc.SetCamera(cam)
+    words = sc.DeviceBuffers().visibility_record_words
+    lists = torch.zeros(2 * E, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(2, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    sc.SetTicketOrigin(0xFFFFFFFF - 150)                # every counter crosses 2^32 within the first frames
+    for frame in range(40):
+        if frame % 2:
+            sc.UpdateWorld()
+            sc.Cull(cam)
+        else:
+            sc.Update()
+        rec = sc.DeviceBuffers().visibility_record
+        sc.ExpandVisible(rec, 1, words, lists.data_ptr(), E, counts.data_ptr(), index_bases=[9])
+        assert np.array_equal(sc.Visible(), ref["visible"]), frame
+        assert counts[0].item() == ref["visible"].size
+        assert np.array_equal(lists[:ref["visible"].size].cpu().numpy().astype(np.uint32), ref["visible"] + 9), frame
+    assert same_values(sc.World(), ref["world"]) and same_values(sc.Mvp(), ref["mvp"])
     sc.Close()

@@ -57,6 +57,111 @@ def test_h8geo_16m_entity_for_entity(oracle, gpu_ctx):
     sc.Close()
 
 
+def _compare_matrices(sc, ref, E, what=("world", "mvp"), step=1 << 21):
+    for first in range(0, E, step):
+        n = min(step, E - first)
+        if "world" in what:
+            w = sc.World(first, n)
+            assert rel_err(w, ref["world"][first:first + n]) <= 1e-5 and same_values(w, ref["world"][first:first + n]), first
+        if "mvp" in what:
+            m = sc.Mvp(first, n)
+            assert rel_err(m, ref["mvp"][first:first + n]) <= 1e-5 and same_values(m, ref["mvp"][first:first + n]), first
+
+
+def test_h8geo_16m_mixed_visibility_cameras(oracle, gpu_ctx):
+    """The 16.7M-entity scene seen from INSIDE (f ~ 0.21: mixed masks in most chunks, the general
+    compaction path) and from far away (wide), entity for entity; the 'mid' camera above is
+    all-or-nothing per root subtree.  One through the fused update, one through a cull pass."""
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 8)
+    E = sum(sizes)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.0)
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.FillSynthetic(BASE_SEED + 3, 8, 0.0)
+    fractions = {}
+    for name, eye, fused in (("inside", (0, 0, 0), True), ("wide", (0, 0, 3000), False), ("oblique", (400, -300, 900), False)):
+        view, proj = camera(oracle, eye=eye)
+        ref = oracle.scene_update(arrays, view, proj, threads=oracle.hardware_threads())
+        cam = zn.Camera(view=view, proj=proj)
+        if fused:
+            sc.SetCamera(cam)
+            sc.Update()
+        else:
+            sc.Cull(cam)
+        vis = sc.Visible()
+        assert np.array_equal(vis, ref["visible"]), name
+        _compare_matrices(sc, ref, E, what=("world", "mvp") if fused else ("mvp",))
+        fractions[name] = vis.size / E
+        # the general path was really taken: plenty of 8192-entity chunks are neither empty nor full
+        flags = np.zeros((E + 8191) // 8192 * 8192, np.uint8)
+        flags[vis] = 1
+        per_chunk = flags.reshape(-1, 8192).sum(axis=1)
+        if name == "inside":
+            assert np.count_nonzero((per_chunk > 0) & (per_chunk < 8192)) > 200
+    assert 0.05 < fractions["inside"] < 0.5 < fractions["wide"]
+    sc.Close()
+
+
+def test_flat_1m_entity_for_entity(oracle, gpu_ctx):
+    """BASELINE configs[1]: 1,048,576 flat entities, three cameras, exact."""
+    import zenyth_b200 as zn
+    E = 1_048_576
+    arrays = oracle.synth_scene(BASE_SEED + 3, [E], fanout=1, center_range=0.0)
+    sc = zn.Scene(gpu_ctx, E)
+    sc.FillSynthetic(BASE_SEED + 3, 1, 0.0)
+    seen = []
+    for eye in ((0, 0, 0), (0, 0, 1500), (0, 0, 3000)):
+        view, proj = camera(oracle, eye=eye)
+        ref = oracle.scene_update(dict(arrays, parent=None, level_offsets=None), view, proj, threads=oracle.hardware_threads())
+        sc.SetCamera(zn.Camera(view=view, proj=proj))
+        sc.Update()
+        vis = sc.Visible()
+        assert np.array_equal(vis, ref["visible"]) and vis.size == sc.VisibleCount()
+        _compare_matrices(sc, ref, E)
+        seen.append(vis.size)
+    assert seen[0] < seen[1] < seen[2]          # per-entity (incoherent) visibility: a flat scene has no subtrees
+    sc.Close()
+
+
+def test_h8geo_32m_scene_with_index_base(oracle, gpu_ctx):
+    """One scene of BASELINE configs[4]: 33,554,430 entities (14 roots), numbered from a non-zero
+    global base as the sharded bench does (scene 3 of 8 would start at 3 * E; any base shows the add)."""
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(14, 8)
+    E = sum(sizes)
+    assert E == 33_554_430
+    base = 3 * E
+    arrays = oracle.synth_scene(BASE_SEED + 5, sizes, fanout=8, center_range=0.0)
+    view, proj = camera(oracle, eye=(0, 0, 1500))
+    ref = oracle.scene_update(arrays, view, proj, threads=oracle.hardware_threads())
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.FillSynthetic(BASE_SEED + 5, 8, 0.0)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    sc.SetIndexBase(base)
+    sc.Update()
+    vis = sc.Visible()
+    assert vis.size == ref["visible"].size and np.array_equal(vis.astype(np.int64), ref["visible"].astype(np.int64) + base)
+    _compare_matrices(sc, ref, E)
+    sc.Close()
+
+
+def test_h8chain_16m_entity_for_entity(oracle, gpu_ctx):
+    """SURVEY §8d stress shape: 8 levels x 2,097,152 entities, fan-out 1 (a distinct parent per child)."""
+    import zenyth_b200 as zn
+    sizes = [2_097_152] * 8
+    E = sum(sizes)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=1, center_range=0.0)
+    view, proj = camera(oracle, eye=(0, 0, 1500))
+    ref = oracle.scene_update(arrays, view, proj, threads=oracle.hardware_threads())
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.FillSynthetic(BASE_SEED + 3, 1, 0.0)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    sc.Update()
+    assert np.array_equal(sc.Visible(), ref["visible"])
+    _compare_matrices(sc, ref, E)
+    sc.Close()
+
+
 def test_mesh_64m_vertices_chunked(oracle, gpu_ctx):
     import zenyth_b200 as zn
     I, verts = 65536, 1024

@@ -120,17 +120,27 @@ import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["ZN_ROOT"])
 import zenyth_b200 as zn
-from zenyth_b200.peer_exchange import PeerRecordExchange
+from zenyth_b200.peer_exchange import PeerExchange, PeerRecordExchange
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(rank)
-dev = torch.device("cuda", rank)
-dist.init_process_group("nccl", device_id=dev)
+# one GPU: both ranks share cuda:0 (CUDA IPC between processes on one device is legal) and gloo carries
+# the handles — NCCL cannot place two ranks on one device; two or more GPUs: one rank each, NCCL
+shared = torch.cuda.device_count() < world
+device_index = 0 if shared else rank
+torch.cuda.set_device(device_index)
+dev = torch.device("cuda", device_index)
+if shared:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=dev)
 stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
-ctx = zn.GpuContext(rank, stream=stream.cuda_stream)
+ctx = zn.GpuContext(device_index, stream=stream.cuda_stream)
+TIMEOUT_MS = 20000 if shared else 2000     # two processes time-slicing one GPU take turns at millisecond granularity
 sizes = [7 * 8 ** l for l in range(7)]
 E = sum(sizes)
 offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
-for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2)):
+for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2), ("library", 1), ("library", 2)):
+    if signal == "nccl" and shared:
+        continue
     scenes, mine = [], []
     for j in range(S):
         sc = zn.Scene(ctx, E, offs)
@@ -140,8 +150,11 @@ for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2)):
         sc.Update()
         mine.append(sc.Visible().astype(np.int64))
         scenes.append(sc)
-    ex = PeerRecordExchange(ctx, scenes[0].DeviceBuffers().visibility_record_words, E, world, rank, dev, torch.int32, signal=signal,
-                            records_per_rank=S)
+    if signal == "library":     # the C++ host layer (zn_exchange_*): torch only carries the 64-byte handles at set-up
+        ex = PeerExchange(ctx, scenes[0].DeviceBuffers().visibility_record_words, E, world, rank, records_per_rank=S, timeout_ms=TIMEOUT_MS)
+    else:
+        ex = PeerRecordExchange(ctx, scenes[0].DeviceBuffers().visibility_record_words, E, world, rank, dev, torch.int32, signal=signal,
+                                records_per_rank=S, timeout_ms=TIMEOUT_MS)
     bases = np.arange(world * S, dtype=np.uint32) * E
     for k in range(9):
         ex.bind(scenes, k)
@@ -167,13 +180,23 @@ print("peer exchange ok", rank)
 
 
 def test_two_processes_exchange_over_peer_memory(tmp_path):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (covered at N = 2..8 by bench.py --exchange peer)")
+    """Two processes over real CUDA IPC: on two GPUs one rank each (NVLink), on ONE GPU both on cuda:0."""
     script = tmp_path / "two_ranks.py"
     script.write_text(_TWO_RANKS)
     env = dict(os.environ, ZN_ROOT=ROOT)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29731", str(script)], env=env, capture_output=True, text=True, timeout=300)
+                          "--master-port", "29731", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert out.stdout.count("peer exchange ok") == 2
+
+
+@pytest.mark.parametrize("world,scenes_per_rank", [(2, 1), (2, 2), (3, 1)])
+def test_cpp_ranks_exchange_without_torch_or_nccl(world, scenes_per_rank):
+    """tests/cpp/exchange_ranks.cpp: fork()ed C++ processes, a socket hub as the host all-gather, Zenyth::PeerExchange,
+    ShardScenes and SceneIndexBases of include/zenyth_b200.hpp — every gathered list of every frame is checked
+    against the single-GPU result inside the program.  Ranks land on GPU rank % device_count."""
+    from zenyth_b200 import build as zb
+    exe = zb.build_cpp_tests()
+    out = subprocess.run([exe, str(world), str(scenes_per_rank), "9", "7"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("exchange ok rank") == world

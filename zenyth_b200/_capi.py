@@ -35,7 +35,7 @@ class SceneBuffers(C.Structure):
 
 class FrameHostIO(C.Structure):
     _fields_ = [("position", vp), ("rotation", vp), ("scale", vp), ("world", vp), ("mvp", vp), ("visible", vp),
-                ("visible_count", C.c_uint32)]
+                ("visible_count", C.c_uint32), ("first", C.c_uint32), ("count", C.c_uint32)]
 
 
 class CullOutput(C.Structure):
@@ -73,6 +73,8 @@ PROTOTYPES = {
     "zn_host_free": (C.c_int, [vp, vp]),
     "zn_device_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "zn_device_free": (C.c_int, [vp, vp]),
+    "zn_device_read": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "zn_device_write": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "zn_ipc_export": (C.c_int, [vp, vp, vp]),
     "zn_ipc_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "zn_ipc_close": (C.c_int, [vp, vp]),
@@ -103,6 +105,7 @@ PROTOTYPES = {
     "zn_scene_update_world": (C.c_int, [vp]),
     "zn_scene_cull": (C.c_int, [vp, vp, vp, C.POINTER(CullOutput)]),
     "zn_scene_clear_camera": (C.c_int, [vp]),
+    "zn_scene_set_ticket_origin": (C.c_int, [vp, C.c_uint32]),
     "zn_scene_cull_times": (C.c_int, [vp, c_float_p, c_float_p]),
     "zn_scene_visible_count": (C.c_int, [vp, c_u32_p]),
     "zn_scene_read_visible": (C.c_int, [vp, vp, C.c_uint32, c_u32_p]),
@@ -170,8 +173,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)   # AttributeError here = the .so does not export a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.zn_abi_version() != 1:
-        raise ImportError(f"libzenyth_b200.so ABI version {lib.zn_abi_version()} != 1")
+    if lib.zn_abi_version() != 2:
+        raise ImportError(f"libzenyth_b200.so ABI version {lib.zn_abi_version()} != 2")
     _lib = lib
     return lib
 

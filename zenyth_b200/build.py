@@ -82,6 +82,28 @@ def build_host(force: bool = False) -> str:
     return HOST_EXE
 
 
+CPP_TEST_SRC = os.path.join(PKG, "..", "tests", "cpp", "exchange_ranks.cpp")
+CPP_TEST_EXE = os.path.join(PKG, "host", "exchange_ranks")
+
+
+def build_cpp_tests(force: bool = False) -> str:
+    """tests/cpp/exchange_ranks.cpp: the C++-only multi-process exchange test (plain g++, no nvcc, no CUDA headers)."""
+    build()
+    inc = os.path.join(PKG, "..", "include")
+    deps = [CPP_TEST_SRC, os.path.join(inc, "zenyth_b200.hpp"), os.path.join(inc, "zenyth_b200.h"), LIB_PATH]
+    if not force and os.path.exists(CPP_TEST_EXE) and all(os.path.getmtime(d) <= os.path.getmtime(CPP_TEST_EXE) for d in deps):
+        return CPP_TEST_EXE
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-I", inc, CPP_TEST_SRC, "-L", LIB_DIR, "-lzenyth_b200",
+           "-Wl,-rpath,$ORIGIN/../lib", "-o", CPP_TEST_EXE]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("g++ failed building exchange_ranks")
+    return CPP_TEST_EXE
+
+
 if __name__ == "__main__":
     print(build(verbose="--verbose" in sys.argv, force=True))
     print(build_host(force=True))
+    print(build_cpp_tests(force=True))

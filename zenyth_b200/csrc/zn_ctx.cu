@@ -169,6 +169,22 @@ int zn_device_free(zn_ctx* ctx, void* ptr) {
 	return ZN_OK;
 }
 
+int zn_device_read(zn_ctx* ctx, const void* dev_ptr, void* host_dst, size_t bytes) {
+	ZN_REQUIRE(ctx && (bytes == 0 || (dev_ptr && host_dst)), "zn_device_read: NULL argument");
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	if (bytes) ZN_CUDA(cudaMemcpyAsync(host_dst, dev_ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	ZN_CUDA(cudaStreamSynchronize(ctx->stream));
+	return ZN_OK;
+}
+
+int zn_device_write(zn_ctx* ctx, void* dev_ptr, const void* host_src, size_t bytes) {
+	ZN_REQUIRE(ctx && (bytes == 0 || (dev_ptr && host_src)), "zn_device_write: NULL argument");
+	ZN_CUDA(cudaSetDevice(ctx->device));
+	if (bytes) ZN_CUDA(cudaMemcpyAsync(dev_ptr, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	ZN_CUDA(cudaStreamSynchronize(ctx->stream));
+	return ZN_OK;
+}
+
 int zn_ipc_export(zn_ctx* ctx, void* dev_ptr, unsigned char out_handle[64]) {
 	ZN_REQUIRE(ctx && dev_ptr && out_handle, "zn_ipc_export: NULL argument");
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

@@ -572,6 +572,19 @@ int zn_scene_cull(zn_scene* s, const float view[16], const float proj[16], const
 	return ZN_OK;
 }
 
+int zn_scene_set_ticket_origin(zn_scene* s, uint32_t origin) {
+	ZN_REQUIRE(s, "zn_scene_set_ticket_origin: scene is NULL");
+	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	ZN_CUDA(cudaStreamSynchronize(s->ctx->stream));
+	std::vector<uint32_t> init(s->levels.size() + 2, origin);
+	ZN_CUDA(cudaMemcpyAsync(s->level_ticket, init.data(), init.size() * 4, cudaMemcpyHostToDevice, s->ctx->stream));
+	ZN_CUDA(cudaStreamSynchronize(s->ctx->stream));
+	for (zn_level& lv : s->levels) lv.ticket_base = origin;
+	s->cull_ticket_base = origin;
+	s->expand_ticket_base = origin;
+	return ZN_OK;
+}
+
 int zn_scene_cull_times(zn_scene* s, float* out_cull_ms, float* out_emit_ms) {
 	ZN_REQUIRE(s && out_cull_ms, "zn_scene_cull_times: NULL argument");
 	if (!s->profiling || !s->cull_events[0]) return fail(ZN_ERR_STATE, "zn_scene_cull_times: profiling is not enabled");
@@ -702,7 +715,9 @@ int zn_scene_frame_host(zn_scene* s, zn_frame_host_io* io) {
 	ZN_REQUIRE(s && io, "zn_scene_frame_host: NULL argument");
 	zn_ctx* ctx = s->ctx;
 	const uint32_t E = s->entity_count;
-	int rc = zn_scene_set_transforms(s, 0, E, io->position, io->rotation, io->scale, 12);
+	ZN_REQUIRE(io->first <= E && uint64_t(io->first) + io->count <= E, "zn_scene_frame_host: range [%u, %u+%u) exceeds entity_count %u", io->first, io->first, io->count, E);
+	const uint32_t n_in = io->count ? io->count : E - io->first;
+	int rc = zn_scene_set_transforms(s, io->first, n_in, io->position, io->rotation, io->scale, 12);
 	if (rc != ZN_OK) return rc;
 	if ((rc = zn_scene_update(s)) != ZN_OK) return rc;
 	ZN_CUDA(cudaMemcpyAsync(s->host_count, s->visible_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -775,8 +790,11 @@ static void pipe_destroy(zn_scene* s) {
 
 int zn_scene_frame_host_submit(zn_scene* s, const zn_frame_host_io* io) {
 	ZN_REQUIRE(s && io, "zn_scene_frame_host_submit: NULL argument");
-	ZN_REQUIRE(io->position && io->rotation && io->scale, "zn_scene_frame_host_submit: position, rotation and scale are required");
 	if (!s->has_camera) return fail(ZN_ERR_STATE, "zn_scene_frame_host_submit: no camera set");
+	ZN_REQUIRE(s->levels.size() <= 63, "zn_scene_frame_host_submit: at most 63 hierarchy levels");
+	const uint32_t E32 = s->entity_count;
+	ZN_REQUIRE(io->first <= E32 && uint64_t(io->first) + io->count <= E32, "zn_scene_frame_host_submit: range [%u, %u+%u) exceeds entity_count %u",
+	           io->first, io->first, io->count, E32);
 	zn_ctx* ctx = s->ctx;
 	ZN_CUDA(cudaSetDevice(ctx->device));
 	int rc = pipe_create(s);
@@ -784,24 +802,26 @@ int zn_scene_frame_host_submit(zn_scene* s, const zn_frame_host_io* io) {
 	zn_pipe* p = s->pipe;
 	if (p->submitted - p->collected >= 2) return fail(ZN_ERR_STATE, "zn_scene_frame_host_submit: two frames are already in flight; call zn_scene_frame_host_wait");
 	const int k = int(p->submitted & 1);
-	const size_t E = s->entity_count, bytes = E * 12;
-	// upload stream: wait until the slot's previous contents have been repacked, then three big copies
-	if (p->submitted >= 2) ZN_CUDA(cudaStreamWaitEvent(p->up, p->repacked[k], 0));
+	const uint32_t n_in = io->count ? io->count : E32 - io->first;
+	const size_t E = s->entity_count, bytes = size_t(n_in) * 12;
 	const float* src[3] = {io->position, io->rotation, io->scale};
-	for (int a = 0; a < 3; ++a)
-		ZN_CUDA(cudaMemcpyAsync(p->staging[k] + a * bytes, src[a], bytes, cudaMemcpyHostToDevice, p->up));
-	ZN_CUDA(cudaEventRecord(p->h2d[k], p->up));
-	// context stream: repack into the tile-major blocks, update into this slot's list buffers
-	ZN_CUDA(cudaStreamWaitEvent(ctx->stream, p->h2d[k], 0));
-	for (int a = 0; a < 3; ++a) {
-		rc = for_each_level_range(s, 0, s->entity_count, [&](const zn_level& lv, uint32_t lo, uint32_t hi) {
-			const uint32_t* from = reinterpret_cast<const uint32_t*>(p->staging[k] + a * bytes) + size_t(lo) * 3;
-			repack3_kernel<<<(hi - lo + 255) / 256, 256, 0, ctx->stream>>>(from, 3, hi - lo, s->blocks, lv.tile_base, lo - lv.begin, 3 * a);
-			return ZN_OK;
-		});
-		if (rc != ZN_OK) return rc;
+	const bool any = (src[0] || src[1] || src[2]) && n_in > 0;
+	if (any) {
+		// upload stream: wait until the slot's previous contents have been repacked, then one copy per array that is present
+		if (p->submitted >= 2) ZN_CUDA(cudaStreamWaitEvent(p->up, p->repacked[k], 0));
+		for (int a = 0; a < 3; ++a)
+			if (src[a]) ZN_CUDA(cudaMemcpyAsync(p->staging[k] + a * E * 12, src[a], bytes, cudaMemcpyHostToDevice, p->up));
+		ZN_CUDA(cudaEventRecord(p->h2d[k], p->up));
+		// context stream: ONE launch scatters the arrays into the tile-major blocks
+		ZN_CUDA(cudaStreamWaitEvent(ctx->stream, p->h2d[k], 0));
+		RepackLevels lv = {};
+		lv.levels = uint32_t(s->levels.size());
+		for (size_t l = 0; l < s->levels.size(); ++l) { lv.begin[l] = s->levels[l].begin; lv.tile_base[l] = s->levels[l].tile_base; }
+		lv.begin[s->levels.size()] = E32;
+		auto at = [&](int a) { return src[a] ? reinterpret_cast<const uint32_t*>(p->staging[k] + a * E * 12) : nullptr; };
+		repack_frame_kernel<<<(n_in + 255) / 256, 256, 0, ctx->stream>>>(at(0), at(1), at(2), io->first, n_in, s->blocks, lv);
+		ZN_CUDA(cudaGetLastError());
 	}
-	ZN_CUDA(cudaGetLastError());
 	ZN_CUDA(cudaEventRecord(p->repacked[k], ctx->stream));
 	uint32_t* keep_vis = s->visible;
 	uint32_t* keep_cnt = s->visible_count;

@@ -771,6 +771,29 @@ __global__ void repack3_kernel(const uint32_t* __restrict__ src, uint32_t stride
 	const uint32_t* s = src + size_t(j) * stride_w;
 	d[0] = s[0]; d[kTile] = s[1]; d[2 * kTile] = s[2];
 }
+// One launch for a whole host frame (zn_scene_frame_host_submit): up to three packed [count][3]
+// arrays (position / rotation / scale, NULL = absent) of entities [first, first+count) into rows
+// 0..8 of the tile-major blocks, across every level the range touches.
+struct RepackLevels {
+	uint32_t begin[64];      // first entity of level l; begin[levels] = entity_count
+	uint32_t tile_base[64];
+	uint32_t levels;
+};
+__global__ void __launch_bounds__(256)
+repack_frame_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ rot, const uint32_t* __restrict__ scl,
+                    uint32_t first, uint32_t count, uint32_t* __restrict__ blocks, const __grid_constant__ RepackLevels lv) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= count) return;
+	const uint32_t e = first + j;
+	uint32_t l = 0;
+	while (l + 1 < lv.levels && e >= lv.begin[l + 1]) ++l;
+	const uint32_t rel = e - lv.begin[l];
+	uint32_t* d = blocks + size_t(lv.tile_base[l] + rel / kTile) * kBlockWords + (rel % kTile);
+	const size_t s = size_t(j) * 3;
+	if (pos) { d[0 * kTile] = pos[s]; d[1 * kTile] = pos[s + 1]; d[2 * kTile] = pos[s + 2]; }
+	if (rot) { d[3 * kTile] = rot[s]; d[4 * kTile] = rot[s + 1]; d[5 * kTile] = rot[s + 2]; }
+	if (scl) { d[6 * kTile] = scl[s]; d[7 * kTile] = scl[s + 1]; d[8 * kTile] = scl[s + 2]; }
+}
 __global__ void repack1_kernel(const uint32_t* __restrict__ src, uint32_t count, uint32_t* __restrict__ blocks,
                                uint32_t tile_base, uint32_t rel_first, int row) {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;

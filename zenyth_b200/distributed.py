@@ -11,26 +11,38 @@ from __future__ import annotations
 from typing import List, Optional, Sequence, Tuple
 
 
+def _lib():
+    from . import _capi
+    return _capi.load()
+
+
+def _check_value(rc: int) -> None:
+    """Host-side argument errors of the C layer surface as ValueError here."""
+    if rc != 0:
+        raise ValueError(_lib().zn_last_error().decode("utf-8", "replace"))
+
+
 def shard_scenes(num_scenes: int, world_size: int, rank: int) -> List[int]:
     """Scene ids owned by `rank`: contiguous blocks, sizes differing by at most one
-    (8 scenes over 1/2/4/8 GPUs -> 8/4/2/1 per GPU; BASELINE.json configs[4])."""
+    (8 scenes over 1/2/4/8 GPUs -> 8/4/2/1 per GPU; BASELINE.json configs[4]).  zn_shard_scenes."""
+    import ctypes as C
     if not (0 <= rank < world_size):
         raise ValueError(f"rank {rank} outside world of {world_size}")
-    base, extra = divmod(num_scenes, world_size)
-    start = rank * base + min(rank, extra)
-    return list(range(start, start + base + (1 if rank < extra else 0)))
+    first, count = C.c_uint32(), C.c_uint32()
+    _check_value(_lib().zn_shard_scenes(num_scenes, world_size, rank, C.byref(first), C.byref(count)))
+    return list(range(first.value, first.value + count.value))
 
 
 def scene_index_bases(entity_counts: Sequence[int]) -> List[int]:
     """Global index base of every scene (exclusive prefix sum) so shard-local visible indices
-    become global by a single add on the device (zn_scene_set_index_base)."""
-    bases, acc = [], 0
-    for n in entity_counts:
-        bases.append(acc)
-        acc += int(n)
-    if acc > 2 ** 32:
-        raise ValueError("global entity index does not fit in 32 bits")
-    return bases
+    become global by a single add on the device (zn_scene_set_index_base).  zn_scene_index_bases."""
+    import ctypes as C
+
+    import numpy as np
+    counts = np.ascontiguousarray(entity_counts, np.uint32)
+    bases = np.zeros(counts.size, np.uint32)
+    _check_value(_lib().zn_scene_index_bases(counts.ctypes.data_as(C.c_void_p), counts.size, bases.ctypes.data_as(C.c_void_p)))
+    return [int(b) for b in bases]
 
 
 NO_PARENT = 0xFFFFFFFF
@@ -86,48 +98,37 @@ def shard_scene_by_roots(arrays: dict, world_size: int) -> List["SceneShard"]:
     Roots (entities without a parent, in any level) are dealt out in index order as contiguous runs
     whose subtree sizes balance the entity counts; every entity follows its root.  Within a shard the
     scene-wide order is kept, so levels stay level-ordered and children stay sorted by parent — the
-    layout contract of zn_scene_set_parents holds for every shard without re-sorting.  Pure host
-    logic over numpy arrays; no arithmetic of the path.
+    layout contract of zn_scene_set_parents holds for every shard without re-sorting.  The partition
+    itself is computed by the C layer (zn_shard_scene_by_roots, the call a C++ engine makes); this
+    wrapper only slices the numpy arrays accordingly.
     """
+    import ctypes as C
+
     import numpy as np
     if world_size < 1:
         raise ValueError("world_size must be >= 1")
-    level_offsets = np.asarray(arrays["level_offsets"], np.int64)
+    level_offsets = np.ascontiguousarray(arrays["level_offsets"], np.uint32)
     E = int(level_offsets[-1])
     parent = arrays.get("parent")
-    parent = np.full(E, NO_PARENT, np.uint32) if parent is None else np.asarray(parent, np.uint32)
-    root = root_of_entities(level_offsets, parent)
-    roots = np.flatnonzero(parent == NO_PARENT)
-    if roots.size < world_size:
-        raise ValueError(f"{roots.size} root subtrees cannot be split over {world_size} ranks")
-    subtree = np.bincount(root, minlength=E)[roots]                   # entities under every root
-    # contiguous runs of roots: root k goes to the rank its cumulative midpoint falls in, then the
-    # cut points are nudged so that no rank is left empty
-    mid = np.cumsum(subtree) - subtree / 2.0
-    owner_of_root = np.minimum((mid * world_size / float(subtree.sum())).astype(np.int64), world_size - 1)
-    owner_of_root = np.maximum.accumulate(owner_of_root)
-    cuts = np.searchsorted(owner_of_root, np.arange(1, world_size))  # first root of ranks 1..W-1
-    for r in range(world_size - 1):                                   # strictly increasing, room for the ranks behind
-        lo = (cuts[r - 1] + 1) if r else 1
-        cuts[r] = min(max(cuts[r], lo), roots.size - (world_size - 1 - r))
-    owner_of_root = np.searchsorted(cuts, np.arange(roots.size), side="right")
-    owner = np.empty(E, np.int64)
-    owner[roots] = owner_of_root
-    owner = owner[root]
-    level_of = np.searchsorted(level_offsets, np.arange(E), side="right") - 1
+    parent = np.full(E, NO_PARENT, np.uint32) if parent is None else np.ascontiguousarray(parent, np.uint32)
+    owner = np.empty(E, np.uint32)
+    local = np.empty(E, np.uint32)
+    counts = np.empty(world_size, np.uint32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    _check_value(_lib().zn_shard_scene_by_roots(vp(level_offsets), level_offsets.size - 1, vp(parent), world_size, vp(owner), vp(local), vp(counts)))
+    level_of = np.searchsorted(level_offsets.astype(np.int64), np.arange(E), side="right") - 1
     shards = []
     for r in range(world_size):
-        mask = owner == r
-        gidx = np.flatnonzero(mask)
-        local = np.cumsum(mask) - 1                                   # scene-wide -> shard-local index
+        gidx = np.flatnonzero(owner == r)
+        assert gidx.size == int(counts[r])
         p = parent[gidx]
         has = p != NO_PARENT
         p_local = np.full(gidx.size, NO_PARENT, np.uint32)
-        p_local[has] = local[p[has].astype(np.int64)].astype(np.uint32)
-        counts = np.bincount(level_of[gidx], minlength=level_offsets.size - 1)
+        p_local[has] = local[p[has].astype(np.int64)]
+        per_level = np.bincount(level_of[gidx], minlength=level_offsets.size - 1)
         # a shard keeps the scene's level order; levels it owns nothing of are dropped (zn_scene_create
         # rejects empty levels) — parents still live in earlier levels, which is all the contract asks
-        offs = np.concatenate([[0], np.cumsum(counts[counts > 0])]).astype(np.uint32)
+        offs = np.concatenate([[0], np.cumsum(per_level[per_level > 0])]).astype(np.uint32)
         a = {k: np.ascontiguousarray(np.asarray(arrays[k])[gidx]) for k in ("position", "rotation", "scale", "aabb_center", "aabb_half")}
         a["parent"] = p_local
         a["level_offsets"] = offs

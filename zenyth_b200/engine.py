@@ -345,15 +345,20 @@ class Scene:
     def ClearCamera(self) -> None:
         check(self._lib.zn_scene_clear_camera(self._h))
 
+    def SetTicketOrigin(self, origin: int) -> None:
+        """Test support: restart the kernels' 32-bit tile-ticket counters at `origin` (zn_scene_set_ticket_origin)."""
+        check(self._lib.zn_scene_set_ticket_origin(self._h, origin & 0xFFFFFFFF))
+
     def CullTimesMs(self):
         """(cull kernel ms, emit kernel ms) of the last Cull; needs SetProfiling(True)."""
         a, b = C.c_float(), C.c_float()
         check(self._lib.zn_scene_cull_times(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def FrameHost(self, position=None, rotation=None, scale=None, world=None, mvp=None, visible=None) -> int:
-        """End-to-end frame with host buffers (zn_scene_frame_host). Returns the visible count."""
-        io = _capi.FrameHostIO(_p(position), _p(rotation), _p(scale), _p(world), _p(mvp), _p(visible), 0)
+    def FrameHost(self, position=None, rotation=None, scale=None, world=None, mvp=None, visible=None, first: int = 0, count: int = 0) -> int:
+        """End-to-end frame with host buffers (zn_scene_frame_host). Returns the visible count.
+        The input arrays cover entities [first, first+count) (count 0: to the end); None = keep what is resident."""
+        io = _capi.FrameHostIO(_p(position), _p(rotation), _p(scale), _p(world), _p(mvp), _p(visible), 0, first, count)
         check(self._lib.zn_scene_frame_host(self._h, C.byref(io)))
         return int(io.visible_count)
 
@@ -382,14 +387,15 @@ class Scene:
         check(self._lib.zn_scene_build_draw(self._h, index_count_per_instance, C.c_void_p(instance_mvp_ptr), instance_capacity,
                                             C.c_void_p(draw_args_ptr)))
 
-    def SubmitFrameHost(self, position, rotation, scale) -> None:
-        """Pipelined end-to-end frame (zn_scene_frame_host_submit): at most two in flight."""
-        io = _capi.FrameHostIO(_p(position), _p(rotation), _p(scale), None, None, None, 0)
+    def SubmitFrameHost(self, position=None, rotation=None, scale=None, first: int = 0, count: int = 0) -> None:
+        """Pipelined end-to-end frame (zn_scene_frame_host_submit): at most two in flight.  Arrays that
+        are None are not uploaded (a frame that only spins its entities passes `rotation` alone)."""
+        io = _capi.FrameHostIO(_p(position), _p(rotation), _p(scale), None, None, None, 0, first, count)
         check(self._lib.zn_scene_frame_host_submit(self._h, C.byref(io)))
 
     def WaitFrameHost(self, visible=None) -> int:
         """Complete the oldest submitted frame; returns its visible count (and fills `visible`)."""
-        io = _capi.FrameHostIO(None, None, None, None, None, _p(visible), 0)
+        io = _capi.FrameHostIO(None, None, None, None, None, _p(visible), 0, 0, 0)
         check(self._lib.zn_scene_frame_host_wait(self._h, C.byref(io)))
         return int(io.visible_count)
 

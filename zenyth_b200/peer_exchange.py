@@ -1,5 +1,14 @@
 """The exchange fused into the compute kernels over NVLink peer memory — no collective on the data path.
 
+Two classes.  `PeerExchange` is the product path: a thin binding of the C++ host layer
+(zn_exchange_* in include/zenyth_b200.h, zenyth_b200/csrc/zn_exchange.cpp) — buffers, CUDA IPC
+rendezvous, per-frame binding arithmetic and the flag-gated expansion all live in the library; the
+only thing Python supplies is the host all-gather callback for the 64-byte handles at set-up
+(torch.distributed here; a C++ engine passes MPI_Allgather or a socket).  `PeerRecordExchange` is the
+earlier torch-hosted statement of the same protocol, kept for the comparison variants bench.py can
+still run (`--exchange peer-nccl`, `peer-waitkernel`) and for the gloo protocol test on fakes.
+The protocol, as both implement it:
+
 Every rank owns ONE plain device allocation
 
     records [slots][world * S][record_words]   gathered visibility records, slot = frame % slots;
@@ -11,11 +20,14 @@ bound to it stores each tile's visibility mask — and, from the emit kernel, th
 straight into slot [rank] of every peer's `records` while its kernels run: plain `st.global` on
 mapped peer pointers, tile by tile (zn_scene_bind_visibility_record + zn_scene_bind_peer_records).
 
-Completion travels the same way (signal="flags", the default): the last CTA of the emit kernel,
-after a system-scope fence, raises flags[rank] in every rank's allocation to the frame's sequence
-number (zn_scene_bind_peer_signal), and the expansion kernel of a frame waits on the owners' flags
-itself (zn_scene_expand_visible_signalled, bounded wait).  No NCCL call, no host synchronisation and
-no extra launch per frame.  signal="nccl" keeps the earlier form — a 4-byte all-reduce per frame as
+Completion travels the same way (signal="flags", the default): the first thread of the kernel that
+FOLLOWS the update on the stream — the next zn_scene_expand_visible_signalled (or zn_scene_wait_flags)
+launch; zn_scene_update itself raises nothing — does one system-scope fence and raises flags[rank] in
+every rank's allocation to the frame's sequence number (zn_scene_bind_peer_signal), and the expansion
+kernel of a frame waits on the owners' flags itself (bounded wait; a record whose owner never
+signals is not expanded).  No NCCL call, no host synchronisation and no extra launch per frame.  The
+LAST frame of a run must therefore be followed by one more expand() call (bench.py's finish()), or its
+peers run into the timeout.  signal="nccl" keeps the earlier form — a 4-byte all-reduce per frame as
 the cross-rank barrier — for comparison.
 
 A rank's OWN lists are not expanded a second time: its scenes' emit kernels write them directly
@@ -34,6 +46,102 @@ from __future__ import annotations
 from typing import List, Optional
 
 FLAG_STRIDE_WORDS = 32          # one 128-byte line per writer
+
+
+class PeerExchange:
+    """zn_exchange_* behind the engine-idiom names (mirrors Zenyth::PeerExchange in zenyth_b200.hpp)."""
+
+    def __init__(self, ctx, record_words: int, capacity: int, world_size: int, rank: int, records_per_rank: int = 1,
+                 slots: int = 4, timeout_ms: int = 2000, allgather=None, group=None):
+        import ctypes as C
+
+        from . import _capi
+        self._lib, self._C, self._capi = _capi.load(), C, _capi
+        self.ctx, self.world_size, self.rank = ctx, int(world_size), int(rank)
+        self.records_per_rank, self.capacity = int(records_per_rank), int(capacity)
+        self.total_records = self.world_size * self.records_per_rank
+        self.timeout_ms = int(timeout_ms)
+        if allgather is None and world_size > 1:
+            allgather = self._torch_allgather(group)
+        self._failed = None
+
+        def trampoline(_user, send, recv, nbytes):
+            try:
+                mine = C.string_at(send, nbytes)
+                parts = allgather(mine)
+                assert len(parts) == self.world_size and all(len(p) == nbytes for p in parts)
+                C.memmove(recv, b"".join(parts), nbytes * self.world_size)
+                return 0
+            except Exception as e:      # noqa: BLE001 - reported through the C layer's status
+                self._failed = e
+                return 1
+
+        self._cb = _capi.ALLGATHER_FN(trampoline if world_size > 1 else (lambda *a: 0))   # kept alive with the object
+        desc = _capi.ExchangeDesc(self.world_size, self.rank, self.records_per_rank, int(record_words), self.capacity, int(slots),
+                                  self.timeout_ms, self._cb, None)
+        h = C.c_void_p()
+        rc = self._lib.zn_exchange_create(ctx._h, C.byref(desc), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(self._lib.zn_last_error().decode("utf-8", "replace"))
+        self._h = h
+
+    @staticmethod
+    def _torch_allgather(group):
+        import torch.distributed as dist
+
+        def gather(mine: bytes):
+            parts = [None] * dist.get_world_size(group)
+            dist.all_gather_object(parts, mine, group=group)
+            return parts
+        return gather
+
+    def _scene_array(self, scenes):
+        scenes = list(scenes) if isinstance(scenes, (list, tuple)) else [scenes]
+        return (self._C.c_void_p * max(len(scenes), 1))(*[s._h for s in scenes]), len(scenes)
+
+    def bind(self, scenes, frame: int) -> None:
+        arr, n = self._scene_array(scenes)
+        self._capi.check(self._lib.zn_exchange_bind(self._h, arr, n, frame))
+
+    def launch(self, frame: int) -> None:      # interface parity with the torch-hosted variants: nothing to launch
+        return None
+
+    def expand(self, scene, frame: int, index_bases=None) -> None:
+        import numpy as np
+        bases = None if index_bases is None else np.ascontiguousarray(index_bases, np.uint32)
+        self._keep = bases
+        self._capi.check(self._lib.zn_exchange_expand(self._h, scene._h, frame, None if bases is None else bases.ctypes.data_as(self._C.c_void_p)))
+
+    def result_raw(self):
+        """(counts, device pointer of lists[total_records][capacity], stride) of the last expanded frame (synchronises)."""
+        import numpy as np
+        C = self._C
+        counts = np.zeros(self.total_records, np.uint32)
+        ptr, stride = C.c_void_p(), C.c_uint32()
+        rc = self._lib.zn_exchange_result(self._h, counts.ctypes.data_as(C.c_void_p), C.byref(ptr), C.byref(stride))
+        if rc != 0:
+            raise RuntimeError(self._lib.zn_last_error().decode("utf-8", "replace"))
+        return [int(c) for c in counts], int(ptr.value), int(stride.value)
+
+    def result(self):
+        """(counts, lists) with lists a zero-copy torch int32 view [total_records, capacity] of the library's buffer."""
+        import torch
+        counts, ptr, stride = self.result_raw()
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (self.total_records * stride,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+        return counts, torch.as_tensor(_View(), device=f"cuda:{self.ctx.device}").view(self.total_records, stride)
+
+    def peer_bytes_per_frame(self) -> int:
+        n = self._C.c_uint64()
+        self._capi.check(self._lib.zn_exchange_info(self._h, None, None, self._C.byref(n)))
+        return int(n.value)
+
+    def close(self, scenes=None) -> None:
+        if getattr(self, "_h", None):
+            arr, n = self._scene_array(scenes) if scenes is not None else (None, 0)
+            self._lib.zn_exchange_destroy(self._h, arr, n)
+            self._h = None
 
 
 class PeerRecordExchange:
@@ -170,7 +278,8 @@ class PeerRecordExchange:
         """(counts, lists[world * records_per_rank, capacity]) of the last expanded frame (synchronises)."""
         status = int(self.status.item())
         if status:
-            raise RuntimeError(f"rank {self.rank}: rank {status - 1} never signalled a frame within {self.timeout_ms} ms")
+            raise RuntimeError(f"rank {self.rank}: rank {(status - 1) // self.records_per_rank} (record {status - 1}) never signalled "
+                               f"a frame within {self.timeout_ms} ms")
         f = self.expanded % 2
         counts = [int(c) for c in self.counts[f * self.total_records: (f + 1) * self.total_records].tolist()]
         return counts, self.lists.view(2, self.total_records, self.capacity)[f]
