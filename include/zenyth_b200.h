@@ -294,7 +294,7 @@ int zn_scene_launches_per_update(zn_scene* scene, uint32_t* out_launches);
 int zn_scene_set_profiling(zn_scene* scene, int enable);
 int zn_scene_level_times(zn_scene* scene, float* out_ms, uint32_t capacity, float* out_tail_ms);
 /* Test support: the persistent kernels claim their tiles from monotonically increasing 32-bit ticket
- * counters (one per level, one for the cull pass, one for the expansion) that wrap after ~2^32
+ * counters (one per level, one for the cull pass) that wrap after ~2^32
  * tickets — every ~74k frames for the last level of the 16M scene.  This call restarts all of them
  * at `origin` (e.g. 0xFFFFFF00) so a test can run a scene across the wrap.  Synchronises. */
 int zn_scene_set_ticket_origin(zn_scene* scene, uint32_t origin);

@@ -4,8 +4,13 @@
 //     exchange_ranks [world=2] [scenes_per_rank=1] [frames=9] [levels=7]
 //
 // Rank r runs on GPU r % device_count, so with ONE GPU both ranks share cuda:0 (CUDA IPC between
-// processes on the same device is legal): peer stores, flag signalling, the bounded wait and the
-// 4-slot / 2-list rotation are exercised exactly as across NVLink.  Every frame uses another camera,
+// processes on the same device is legal): IPC mapping, peer stores, flag stores and acquire loads
+// and the 4-slot / 2-list rotation are exercised exactly as across NVLink.  Ranks that SHARE a GPU
+// run in lockstep (stream sync + host rendezvous after every frame), so that no kernel ever has to
+// spin on a flag another process on the same GPU has yet to raise — kernels of different processes
+// on one device are not guaranteed to run at the same time, and a spinning kernel can starve the
+// one it waits for (Xid 109 on this driver).  With one GPU per rank nothing is synchronised on the
+// host and the flags are waited on by the device, as in production.  Every frame uses another camera,
 // and every rank checks EVERY gathered list of EVERY frame against the list a plain single-GPU
 // update of that scene produces.  The parent never touches CUDA (fork before any CUDA call).
 #include "zenyth_b200.hpp"
@@ -77,6 +82,7 @@ static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int 
 		int devices = 0;
 		if (zn_device_count(&devices) != ZN_OK || devices < 1) { std::fprintf(stderr, "rank %u: no CUDA device\n", rank); return 3; }
 		GpuContext ctx(int(rank) % devices);
+		const bool lockstep = uint32_t(devices) < world;     // some ranks share a GPU
 		SceneDesc desc;
 		desc.levelOffsets.push_back(0);
 		for (int l = 0, n = 7; l < levels; ++l, n *= 8) desc.levelOffsets.push_back(desc.levelOffsets.back() + uint32_t(n));
@@ -113,7 +119,7 @@ static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int 
 		Channel ch{fd, world};
 		PeerExchangeDesc xd;
 		xd.worldSize = world; xd.rank = rank; xd.recordsPerRank = S; xd.allGather = all_gather; xd.user = &ch; xd.indexBases = bases;
-		xd.timeoutMs = 20000;   // two processes time-slicing ONE GPU take turns at millisecond granularity
+		xd.timeoutMs = 5000;
 		{
 			PeerExchange exchange(ctx, *scenes[0], xd);
 			std::vector<uint32_t> host;
@@ -134,11 +140,18 @@ static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int 
 				}
 				return true;
 			};
+			auto rendezvous = [&]() {
+				ctx.Sync();
+				uint32_t token = rank;
+				std::vector<uint32_t> all(world);
+				return all_gather(&ch, &token, all.data(), 4) == 0;
+			};
 			for (int k = 0; k < frames; ++k) {
 				const Camera cam(camera_of_frame(k));
 				exchange.Bind(ptrs, uint64_t(k));
 				for (Scene* s : ptrs) { s->SetCamera(cam); s->Update(); }
-				exchange.Expand(k - 1);
+				exchange.Expand(k - 1);     // raises this rank's frame-k flags; waits (on the device) for the peers' frame k-1 flags
+				if (lockstep && !rendezvous()) return 6;   // shared GPU: every flag the next launch waits for is up before it starts
 				if (k >= 1 && !verify(k - 1)) return 5;
 			}
 			exchange.Expand(frames - 1);

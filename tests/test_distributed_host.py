@@ -190,13 +190,15 @@ def _peer_worker(rank: int, world: int, port: int, out_dir: str):
     ok &= ex.expand(sc, 5) and not ex.expand(sc, 6)   # never issued
     names = [c[0] for c in sc.calls]
     ok &= names[:6] == ["BindPeerSignal", "BindVisibilityRecord", "BindPeerRecords", "BindVisibleOutput", "SetSignalValue", "Update"]
-    ok &= names.count("BindPeerSignal") == 1 and names.count("ExpandVisibleSignalled") == 6
+    ok &= names.count("BindPeerSignal") == 1 and names.count("ExpandVisibleSignalled") == 7   # 6 frames + the signal-only launch after frame 0
     binds = [c for c in sc.calls if c[0] == "BindVisibilityRecord"]
     peers = [c for c in sc.calls if c[0] == "BindPeerRecords"]
     for k in range(6):
         off = (k % 4) * slot_bytes + rank * words * 4
         ok &= binds[k][1] == (own + off,) and peers[k][1] == ([peer + off],)
     expands = [c for c in sc.calls if c[0] == "ExpandVisibleSignalled"]
+    first = expands.pop(0)                         # after frame 0: every record skipped, nothing expected — it only raises the flags
+    ok &= first[2]["skip_index"] == 0 and first[2]["skip_count"] == world and first[1][8] == 0
     for k, c in enumerate(expands):                 # frame k: slot k%4, list half k%2, waits for sequence k+1, skips itself
         a, kw = c[1], c[2]
         ok &= a[0] == own + (k % 4) * slot_bytes and a[1:3] == (world, words)
@@ -220,7 +222,7 @@ def _peer_worker(rank: int, world: int, port: int, out_dir: str):
         outs = [c[1] for c in sc.calls if c[0] == "BindVisibleOutput"]
         ok &= [o[0] for o in outs] == [ex.lists.data_ptr() + ((k % 2) * world * 2 + rank * 2 + j) * cap * 4 for k in range(3)]
     ok &= [c[0] for c in b.calls].count("BindPeerSignal") == 0 and [c[0] for c in b.calls].count("SetSignalValue") == 0
-    e = [c for c in a.calls if c[0] == "ExpandVisibleSignalled"]
+    e = [c for c in a.calls if c[0] == "ExpandVisibleSignalled"][1:]     # [0] is the signal-only launch after frame 0
     ok &= len(e) == 2 and all(c[1][1] == world * 2 for c in e)
     ok &= all(c[2]["skip_index"] == rank * 2 and c[2]["skip_count"] == 2 and c[2]["records_per_flag"] == 2 for c in e)
     ex.close([a, b])

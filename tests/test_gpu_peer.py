@@ -123,7 +123,12 @@ import zenyth_b200 as zn
 from zenyth_b200.peer_exchange import PeerExchange, PeerRecordExchange
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 # one GPU: both ranks share cuda:0 (CUDA IPC between processes on one device is legal) and gloo carries
-# the handles — NCCL cannot place two ranks on one device; two or more GPUs: one rank each, NCCL
+# the handles — NCCL cannot place two ranks on one device; two or more GPUs: one rank each, NCCL.
+# Ranks that share a GPU run in LOCKSTEP (device sync + host barrier after every frame): kernels of
+# different processes on one device are not guaranteed to run at the same time, so no kernel may have
+# to spin on a flag the other process has yet to raise (a spinning kernel can starve the one it waits
+# for: Xid 109 on this driver).  IPC mapping, peer stores, flag stores / acquire loads and the slot
+# rotation are exercised all the same; with a GPU per rank the device does the waiting, as in production.
 shared = torch.cuda.device_count() < world
 device_index = 0 if shared else rank
 torch.cuda.set_device(device_index)
@@ -134,7 +139,7 @@ else:
     dist.init_process_group("nccl", device_id=dev)
 stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
 ctx = zn.GpuContext(device_index, stream=stream.cuda_stream)
-TIMEOUT_MS = 20000 if shared else 2000     # two processes time-slicing one GPU take turns at millisecond granularity
+TIMEOUT_MS = 5000 if shared else 2000
 sizes = [7 * 8 ** l for l in range(7)]
 E = sum(sizes)
 offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
@@ -162,6 +167,9 @@ for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2), ("library", 1), ("lib
             sc.Update()
         ex.launch(k)
         ex.expand(scenes[0], k - 1, bases)
+        if shared:
+            torch.cuda.synchronize(dev)
+            dist.barrier()
     ex.expand(scenes[0], 8, bases)
     counts, lists = ex.result()
     every = [None] * world

@@ -295,6 +295,13 @@ int zn_exchange_bind(zn_exchange* x, zn_scene* const* scenes, uint32_t scene_cou
 
 int zn_exchange_expand(zn_exchange* x, zn_scene* scene, int64_t frame, const uint32_t* index_bases) {
 	ZN_REQUIRE(x && scene, "zn_exchange_expand: NULL argument");
+	if (frame < 0 && x->issued == 0 && x->expanded < 0) {
+		// Frame 0 has been updated and there is nothing to expand yet: a signal-only launch (every record
+		// skipped) raises its flags now instead of one frame later, so no peer ever waits on this rank's
+		// first flag longer than it must.
+		return zn_scene_expand_visible_signalled(scene, x->base, x->total, x->record_words, 0, x->total, nullptr, x->lists, x->capacity, x->counts,
+		                                         x->base + x->flags_offset, kFlagStrideWords, x->per_rank, 0u, x->timeout_ms, x->status);
+	}
 	if (frame < 0 || frame > x->issued || frame <= x->expanded) return ZN_OK;   // never issued, or already expanded
 	ZN_REQUIRE(frame == x->expanded + 1, "zn_exchange_expand: frames are expanded in order (expected %lld)", (long long)(x->expanded + 1));
 	const uint8_t* records = x->base + size_t(frame % x->slots) * x->slot_bytes;

@@ -68,6 +68,8 @@ struct zn_scene {
 	bool world_valid = false;      // an update has run: the world matrices exist (zn_scene_cull needs them)
 	bool last_update_had_view = false;
 	bool ranges_dirty = true;      // tile_prange must be rebuilt before the next update
+	bool inputs_touched = true;    // an upload / fill has written the input blocks since the last update: level 0 must not
+	                               // start its first block load early (programmatic launch) behind the kernel that wrote them
 	float view_proj[16];
 	float planes[24];
 	// inputs: one 16 KiB block per 256-entity tile, rows = tx,ty,tz, pitch,yaw,roll, sx,sy,sz,
@@ -93,12 +95,10 @@ struct zn_scene {
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
 	uint32_t* chunk_total = nullptr;       // [2][chunks] visible count per chunk, one set per frame parity
 	uint32_t frame_parity = 0;
-	uint32_t* level_ticket = nullptr;      // [levels + 2] monotonically increasing tickets: one counter per level, then the
-	                                       // cull pass's tile counter and the expansion's item counter
-	uint32_t cull_ticket_base = 0;         // tickets the cull / expansion counters have handed out in earlier launches
-	uint32_t expand_ticket_base = 0;
-	int max_ctas_cull = 0;                 // co-resident CTAs of scene_cull_kernel / expand_visible_kernel
-	int max_ctas_expand = 0;
+	uint32_t* level_ticket = nullptr;      // [levels + 1] monotonically increasing tickets: one counter per level, then the
+	                                       // cull pass's tile counter
+	uint32_t cull_ticket_base = 0;         // tickets the cull counter has handed out in earlier launches
+	int max_ctas_cull = 0;                 // co-resident CTAs of scene_cull_kernel
 	CUtensorMap tm_world_all, tm_mvp_all;  // all E rows (the cull pass is one launch over every level)
 	std::vector<std::pair<void*, CUtensorMap>> mvp_maps;   // tensor maps of caller-owned MVP arrays (zn_scene_cull)
 	const void* abort_status = nullptr;    // status word of the last zn_scene_wait_flags, consumed by the next plain expansion
@@ -129,7 +129,9 @@ struct zn_mesh {
 	float* nrm_out = nullptr;
 	float* models_own = nullptr;     // [I][16]
 	uint32_t* instance_first_vertex = nullptr;  // device [I+1]
-	float* inst_mats = nullptr;      // [I][24] model rows + normal matrix, only when a tile spans several instances
+	float* inst_mats = nullptr;      // [I][24] model rows + normal matrix, only when some tile holds more instances than its shared-memory window
 	bool multi_instance_tiles = false;
+	bool needs_inst_mats = false;
+	uint32_t smem_window = 0;        // most instances any multi-instance tile touches (<= 1024): sizes the kernel's dynamic shared memory
 	const float* models = nullptr;   // models_own or a scene's world array
 };

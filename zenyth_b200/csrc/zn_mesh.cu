@@ -11,9 +11,14 @@
 // a global load or store for vertex data, and HBM only sees 12 KiB bursts.
 //   - a tile inside ONE instance (the common case for large meshes): thread 32 inverts that
 //     instance's model matrix while the copies are in flight;
-//   - a tile spanning SEVERAL instances (small meshes): the per-instance matrices come from a table
-//     built by mesh_instance_mats_kernel, and a thread finds each vertex's instance by binary
-//     search over the tile's slice of instance_first_vertex staged in shared memory.
+//   - a tile spanning SEVERAL instances (small meshes): while the copies are in flight, thread k
+//     inverts the k-th instance's model matrix into shared memory (up to 256 instances per tile: no
+//     matrix table in HBM, 64 B read per instance instead of 64 + 96 + 96) and every thread finds the
+//     instance of its FIRST vertex by binary search over the tile's slice of instance_first_vertex
+//     in shared memory; its other three vertices advance linearly from there.  The shared window is
+//     sized per mesh (dynamic shared memory: the most instances any of its tiles touches, up to
+//     1024 — one vertex per instance); only tiles that touch more than that (through runs of EMPTY
+//     instances) fall back to a per-instance matrix table built by mesh_instance_mats_kernel.
 #include "zn_internal.hpp"
 #include "zn_math.cuh"
 #include "zn_ptx.cuh"
@@ -24,8 +29,10 @@
 namespace zn {
 
 constexpr int kMeshThreads = kMeshTileVerts / 4;
-constexpr uint32_t kMeshSmemInstances = 512;   // instance boundaries of a tile staged in shared memory
-constexpr int kInstMatFloats = 24;             // rows 0..2 of the model (12) + 3x3 normal matrix (9) + 3 pad
+constexpr uint32_t kMeshSmemMats = 1024;       // most instances of one tile whose matrices / boundaries are kept in shared memory
+                                               // (a 1024-vertex tile touches more only through EMPTY instances)
+constexpr int kSmemMatFloats = 21;             // rows 0..2 of the model (12) + 3x3 normal matrix (9); odd stride: conflict-free
+constexpr int kInstMatFloats = 24;             // the same in global memory (tiles with > kMeshSmemMats instances), padded to 16 bytes
 
 // Per-instance matrices for tiles that span several instances.
 __global__ void mesh_instance_mats_kernel(const float* __restrict__ models, uint32_t instances, float* __restrict__ out) {
@@ -72,21 +79,39 @@ __global__ void __launch_bounds__(kMeshThreads, 4)
 mesh_tile_kernel(const zn_mesh_tile* __restrict__ tiles, const float* __restrict__ models,
                  const uint32_t* __restrict__ instance_first_vertex, const float* __restrict__ inst_mats,
                  const float* __restrict__ pos_in, const float* __restrict__ nrm_in,
-                 float* __restrict__ pos_out, float* __restrict__ nrm_out) {
+                 float* __restrict__ pos_out, float* __restrict__ nrm_out, uint32_t window) {
 	__shared__ __align__(128) float s_pos[kMeshTileVerts * 3];
 	__shared__ __align__(128) float s_nrm[kMeshTileVerts * 3];
 	__shared__ float s_model[12];   // rows 0..2 of the model, row-major [r*4+c]
 	__shared__ float s_nm[9];       // upper 3x3 of (model^-1)^T, row-major
-	__shared__ uint32_t s_first[MULTI ? kMeshSmemInstances + 1 : 1];
+	extern __shared__ uint32_t s_dyn[];   // MULTI: first[window + 1], then mats[window][21]
+	uint32_t* s_first = s_dyn;
+	float* s_mats = reinterpret_cast<float*>(s_dyn + window + 1);
 	__shared__ uint64_t s_bar;
 
 	const int t = threadIdx.x;
 	const zn_mesh_tile tile = tiles[blockIdx.x];
 	const bool single = !MULTI || tile.instance_lo == tile.instance_hi;
 	const uint32_t n_inst = tile.instance_hi - tile.instance_lo + 1u;
-	const bool staged = n_inst <= kMeshSmemInstances;
+	const bool staged = MULTI && n_inst <= window;
+	const bool smem_mats = staged;
 	const uint32_t floats = ((tile.vertex_count + 3u) & ~3u) * 3u;   // whole 4-vertex groups: a multiple of 16 bytes
 	const size_t base = size_t(tile.first_vertex) * 3;
+
+	// Model rows + normal matrix of one instance: M[r*4+c] = model(r,c), N[r*3+c] = inverse(c,r).
+	auto instance_matrices = [&](const float4* col, float* M, float* N) {
+		float m[16], inv[16];
+#pragma unroll
+		for (int c = 0; c < 4; ++c) { m[c * 4 + 0] = col[c].x; m[c * 4 + 1] = col[c].y; m[c * 4 + 2] = col[c].z; m[c * 4 + 3] = col[c].w; }
+		mat4_inverse(m, inv);
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+#pragma unroll
+			for (int c = 0; c < 4; ++c) M[r * 4 + c] = m[c * 4 + r];
+#pragma unroll
+			for (int c = 0; c < 3; ++c) N[r * 3 + c] = inv[r * 4 + c];   // transpose(inverse)(r,c) = inverse(c,r)
+		}
+	};
 
 	if (t == 0) {
 		mbar_init(&s_bar, 1);
@@ -95,25 +120,45 @@ mesh_tile_kernel(const zn_mesh_tile* __restrict__ tiles, const float* __restrict
 		bulk_g2s(s_pos, pos_in + base, floats * 4, &s_bar);
 		bulk_g2s(s_nrm, nrm_in + base, floats * 4, &s_bar);
 	} else if (t == 32 && single) {
-		float m[16], inv[16];
 		const float4* src = reinterpret_cast<const float4*>(models + size_t(tile.instance_lo) * 16);
-#pragma unroll
-		for (int c = 0; c < 4; ++c) {
-			const float4 col = __ldg(src + c);
-			m[c * 4 + 0] = col.x; m[c * 4 + 1] = col.y; m[c * 4 + 2] = col.z; m[c * 4 + 3] = col.w;
-		}
-		mat4_inverse(m, inv);
-#pragma unroll
-		for (int r = 0; r < 3; ++r) {
-#pragma unroll
-			for (int c = 0; c < 4; ++c) s_model[r * 4 + c] = m[c * 4 + r];
-#pragma unroll
-			for (int c = 0; c < 3; ++c) s_nm[r * 3 + c] = inv[r * 4 + c];   // transpose(inverse)(r,c) = inverse(c,r)
-		}
+		const float4 col[4] = {__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3)};
+		instance_matrices(col, s_model, s_nm);
 	}
-	if (!single && staged)
-		for (uint32_t k = t; k <= n_inst; k += kMeshThreads) s_first[k] = __ldg(instance_first_vertex + tile.instance_lo + k);
+	// ---- while the copies are in flight: instance boundaries, per-instance matrices, first-vertex search ----
+	if (MULTI && !single) {
+		if (staged)
+			for (uint32_t k = t; k <= n_inst; k += kMeshThreads) s_first[k] = __ldg(instance_first_vertex + tile.instance_lo + k);
+		if (smem_mats)
+			for (uint32_t k = t; k < n_inst; k += kMeshThreads) {
+				// an instance without a vertex in this tile (empty, or all its vertices behind the tile's end) needs no matrix;
+				// the model is fetched alongside the two boundaries (one round trip), the inverse only computed if needed
+				const uint32_t lo = max(__ldg(instance_first_vertex + tile.instance_lo + k), tile.first_vertex);
+				const uint32_t hi = min(__ldg(instance_first_vertex + tile.instance_lo + k + 1), tile.first_vertex + tile.vertex_count);
+				const float4* src = reinterpret_cast<const float4*>(models + size_t(tile.instance_lo + k) * 16);
+				const float4 col[4] = {__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3)};
+				if (lo >= hi) continue;
+				float M[12], N[9];
+				instance_matrices(col, M, N);
+				float* o = s_mats + k * kSmemMatFloats;
+#pragma unroll
+				for (int i = 0; i < 12; ++i) o[i] = M[i];
+#pragma unroll
+				for (int i = 0; i < 9; ++i) o[12 + i] = N[i];
+			}
+	}
 	__syncthreads();
+	auto first_of = [&](uint32_t k) { return staged ? s_first[k] : __ldg(instance_first_vertex + tile.instance_lo + k); };
+	uint32_t inst = 0;
+	if (MULTI && !single && uint32_t(t) * 4 < tile.vertex_count) {
+		// instance of this thread's first vertex: the last k in [0, n_inst) with first[k] <= vertex
+		const uint32_t vertex = tile.first_vertex + uint32_t(t) * 4;
+		uint32_t lo = 0, hi = n_inst - 1;
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi + 1) >> 1;
+			if (first_of(mid) <= vertex) lo = mid; else hi = mid - 1;
+		}
+		inst = lo;
+	}
 	mbar_wait(&s_bar, 0);
 
 	if (uint32_t(t) * 4 < tile.vertex_count) {
@@ -135,22 +180,24 @@ mesh_tile_kernel(const zn_mesh_tile* __restrict__ tiles, const float* __restrict
 			uint32_t have = 0xFFFFFFFFu;
 #pragma unroll
 			for (int v = 0; v < 4; ++v) {
-				// instance of this vertex: the last k in [0, n_inst) with first[k] <= vertex
 				const uint32_t vertex = tile.first_vertex + uint32_t(t) * 4 + v;
-				uint32_t lo = 0, hi = n_inst - 1;
-				while (lo < hi) {
-					const uint32_t mid = (lo + hi + 1) >> 1;
-					const uint32_t f = staged ? s_first[mid] : __ldg(instance_first_vertex + tile.instance_lo + mid);
-					if (f <= vertex) lo = mid; else hi = mid - 1;
-				}
-				if (lo != have) {
-					const float4* src = reinterpret_cast<const float4*>(inst_mats + size_t(tile.instance_lo + lo) * kInstMatFloats);
+				while (inst + 1 < n_inst && first_of(inst + 1) <= vertex) ++inst;   // the next vertices advance from the first one's instance
+				if (inst != have) {
+					if (smem_mats) {
+						const float* src = s_mats + inst * kSmemMatFloats;
 #pragma unroll
-					for (int k = 0; k < 3; ++k) { const float4 r = __ldg(src + k); M[4 * k] = r.x; M[4 * k + 1] = r.y; M[4 * k + 2] = r.z; M[4 * k + 3] = r.w; }
-					const float4 r3 = __ldg(src + 3), r4 = __ldg(src + 4);
-					const float r5 = __ldg(reinterpret_cast<const float*>(src + 5));
-					N[0] = r3.x; N[1] = r3.y; N[2] = r3.z; N[3] = r3.w; N[4] = r4.x; N[5] = r4.y; N[6] = r4.z; N[7] = r4.w; N[8] = r5;
-					have = lo;
+						for (int k = 0; k < 12; ++k) M[k] = src[k];
+#pragma unroll
+						for (int k = 0; k < 9; ++k) N[k] = src[12 + k];
+					} else {
+						const float4* src = reinterpret_cast<const float4*>(inst_mats + size_t(tile.instance_lo + inst) * kInstMatFloats);
+#pragma unroll
+						for (int k = 0; k < 3; ++k) { const float4 r = __ldg(src + k); M[4 * k] = r.x; M[4 * k + 1] = r.y; M[4 * k + 2] = r.z; M[4 * k + 3] = r.w; }
+						const float4 r3 = __ldg(src + 3), r4 = __ldg(src + 4);
+						const float r5 = __ldg(reinterpret_cast<const float*>(src + 5));
+						N[0] = r3.x; N[1] = r3.y; N[2] = r3.z; N[3] = r3.w; N[4] = r4.x; N[5] = r4.y; N[6] = r4.z; N[7] = r4.w; N[8] = r5;
+					}
+					have = inst;
 				}
 				transform_vertex(M, N, p + 3 * v, n + 3 * v);
 			}
@@ -226,7 +273,8 @@ int zn_mesh_create(zn_ctx* ctx, const zn_mesh_desc* desc, zn_mesh** out_mesh) {
 	}
 	// tiles of 1024 vertices over the whole stream; [instance_lo, instance_hi] = the instances a tile touches
 	std::vector<zn_mesh_tile> tiles;
-	bool multi = false;
+	bool multi = false, table = false;
+	uint32_t window = 0;
 	{
 		uint32_t k = 0;
 		for (uint32_t v = 0; v < V; v += kMeshTileVerts) {
@@ -239,6 +287,10 @@ int zn_mesh_create(zn_ctx* ctx, const zn_mesh_desc* desc, zn_mesh** out_mesh) {
 			while (h + 1 < I && first[h + 1] <= v + t.vertex_count - 1) ++h; // last instance starting inside the tile
 			t.instance_hi = h;
 			multi = multi || (h != k);
+			if (h != k) {
+				if (h - k + 1 > kMeshSmemMats) table = true;
+				else window = std::max(window, h - k + 1);
+			}
 			tiles.push_back(t);
 		}
 	}
@@ -261,7 +313,9 @@ int zn_mesh_create(zn_ctx* ctx, const zn_mesh_desc* desc, zn_mesh** out_mesh) {
 	ZN_TRY(cudaMalloc(&m->instance_first_vertex, (size_t(I) + 1) * 4));
 	ZN_TRY(cudaMemcpyAsync(m->instance_first_vertex, first.data(), (size_t(I) + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
 	m->multi_instance_tiles = multi;
-	if (multi) ZN_TRY(cudaMalloc(&m->inst_mats, size_t(I) * kInstMatFloats * 4));
+	m->needs_inst_mats = table;
+	m->smem_window = window;
+	if (table) ZN_TRY(cudaMalloc(&m->inst_mats, size_t(I) * kInstMatFloats * 4));
 	ZN_TRY(cudaMalloc(&m->models_own, size_t(I) * 64));
 	ZN_TRY(cudaMemcpyAsync(m->tiles, tiles.data(), tiles.size() * sizeof(zn_mesh_tile), cudaMemcpyHostToDevice, ctx->stream));
 	ZN_TRY(cudaMemsetAsync(m->models_own, 0, size_t(I) * 64, ctx->stream));
@@ -316,14 +370,17 @@ int zn_mesh_bind_scene_models(zn_mesh* m, zn_scene* scene, uint32_t first_entity
 int zn_mesh_transform(zn_mesh* m) {
 	ZN_REQUIRE(m, "zn_mesh_transform: mesh is NULL");
 	ZN_CUDA(cudaSetDevice(m->ctx->device));
-	if (m->multi_instance_tiles)
+	if (m->needs_inst_mats)
 		mesh_instance_mats_kernel<<<(m->instance_count + 127) / 128, 128, 0, m->ctx->stream>>>(m->models, m->instance_count, m->inst_mats);
-	if (m->multi_instance_tiles)
-		mesh_tile_kernel<true><<<m->tile_count, kMeshThreads, 0, m->ctx->stream>>>(m->tiles, m->models, m->instance_first_vertex, m->inst_mats,
-		                                                                          m->pos_in, m->nrm_in, m->pos_out, m->nrm_out);
-	else
-		mesh_tile_kernel<false><<<m->tile_count, kMeshThreads, 0, m->ctx->stream>>>(m->tiles, m->models, m->instance_first_vertex, m->inst_mats,
-		                                                                           m->pos_in, m->nrm_in, m->pos_out, m->nrm_out);
+	if (m->multi_instance_tiles) {
+		const size_t dyn = (size_t(m->smem_window) + 1) * 4 + size_t(m->smem_window) * kSmemMatFloats * 4;
+		ZN_CUDA(cudaFuncSetAttribute(mesh_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn)));
+		mesh_tile_kernel<true><<<m->tile_count, kMeshThreads, dyn, m->ctx->stream>>>(m->tiles, m->models, m->instance_first_vertex, m->inst_mats,
+		                                                                            m->pos_in, m->nrm_in, m->pos_out, m->nrm_out, m->smem_window);
+	} else {
+		mesh_tile_kernel<false><<<m->tile_count, kMeshThreads, 4, m->ctx->stream>>>(m->tiles, m->models, m->instance_first_vertex, m->inst_mats,
+		                                                                           m->pos_in, m->nrm_in, m->pos_out, m->nrm_out, 0u);
+	}
 	ZN_CUDA(cudaGetLastError());
 	return ZN_OK;
 }

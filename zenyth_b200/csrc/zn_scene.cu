@@ -49,6 +49,7 @@ static int for_each_level_range(zn_scene* s, uint32_t first, uint32_t count, F&&
 static int upload3(zn_scene* s, int row0, uint32_t first, uint32_t count, const float* host, size_t stride_bytes) {
 	if (!host || count == 0) return ZN_OK;
 	zn_ctx* ctx = s->ctx;
+	s->inputs_touched = true;
 	const uint32_t stride_w = uint32_t(stride_bytes / 4);
 	const uint32_t chunk = 1u << 22;   // records per pass: <= 64 MiB of staging at stride 16
 	int rc = ensure_staging(ctx, size_t(std::min(count, chunk)) * stride_bytes);
@@ -116,15 +117,13 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	s->ctx = ctx;
 	s->entity_count = E;
 	// Persistent grid: as many CTAs as fit at once.
-	int per_sm_a = 0, per_sm_b = 0, per_sm_c = 0, per_sm_d = 0;
+	int per_sm_a = 0, per_sm_b = 0, per_sm_c = 0;
 	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, scene_level_kernel<true, true>, kTile, kLevelSmem));
 	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, scene_level_kernel<false, true>, kTile, kLevelSmem));
 	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, scene_cull_kernel, kTile, kCullSmem));
-	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, expand_visible_kernel, kExpandWarps * 32, 0));
 	s->max_ctas = std::min(per_sm_a, per_sm_b) * ctx->sm_count;
 	s->max_ctas_cull = per_sm_c * ctx->sm_count;
-	s->max_ctas_expand = per_sm_d * ctx->sm_count;
-	if (s->max_ctas < 1 || s->max_ctas_cull < 1 || s->max_ctas_expand < 1) { delete s; return fail(ZN_ERR_CUDA, "zn_scene_create: a scene kernel does not fit on an SM"); }
+	if (s->max_ctas < 1 || s->max_ctas_cull < 1) { delete s; return fail(ZN_ERR_CUDA, "zn_scene_create: a scene kernel does not fit on an SM"); }
 	uint32_t tile_base = 0;
 	std::vector<uint32_t> tile_first;
 	for (size_t l = 0; l + 1 < offs.size(); ++l) {
@@ -150,8 +149,8 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	s->visible = s->visible_own;
 	s->visible_count = s->visible_count_own;
 	ZN_TRY(cudaMalloc(&s->chunk_total, size_t(s->chunk_count) * 2 * 4));   // two sets, by frame parity
-	ZN_TRY(cudaMalloc(&s->level_ticket, (s->levels.size() + 2) * 4));
-	ZN_TRY(cudaMemsetAsync(s->level_ticket, 0, (s->levels.size() + 2) * 4, ctx->stream));
+	ZN_TRY(cudaMalloc(&s->level_ticket, (s->levels.size() + 1) * 4));
+	ZN_TRY(cudaMemsetAsync(s->level_ticket, 0, (s->levels.size() + 1) * 4, ctx->stream));
 	s->record_words = record_header_words(s->chunk_count) + s->tile_count * kWarpsPerTile;
 	ZN_TRY(cudaMalloc(&s->record_own, size_t(s->record_words) * 4));
 	ZN_TRY(cudaMemsetAsync(s->record_own, 0, size_t(s->record_words) * 4, ctx->stream));
@@ -258,6 +257,7 @@ int zn_scene_set_parents(zn_scene* s, uint32_t first, uint32_t count, const uint
 		ZN_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's array may be pageable and reused
 	}
 	s->ranges_dirty = true;
+	s->inputs_touched = true;
 	return ZN_OK;
 }
 
@@ -337,17 +337,14 @@ static int expand_visible(zn_scene* s, const char* who, const void* records_dev,
 		for (uint32_t* flag : s->peer_flags) sig.flag[sig.n++] = flag;
 		sig.value = s->signal_value;
 	}
-	// Persistent grid of autonomous warps drawing (record, chunk) items from a ticket counter: one draw
-	// per item plus one per warp (the draw that tells it to stop).
-	const uint32_t items = (record_count - skip_count) * s->chunk_count;
-	const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>((items + kExpandWarps - 1) / kExpandWarps, uint32_t(s->max_ctas_expand)));
-	uint32_t* ticket = s->level_ticket + s->levels.size() + 1;
+	// One warp per chunk, eight per CTA, one grid row per expanded record.
+	const dim3 grid((s->chunk_count + kExpandWarps - 1) / kExpandWarps, std::max<uint32_t>(1u, record_count - skip_count));
+	if (record_count == skip_count && !flags_dev) return ZN_OK;     // nothing to expand and nothing to signal
 	expand_visible_kernel<<<grid, kExpandWarps * 32, 0, s->ctx->stream>>>(
 		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count,
 		skip_index, int(skip_count), static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),
 		static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag, uint64_t(timeout_ms) * 1000000ull,
-		static_cast<uint32_t*>(status_dev), static_cast<const uint32_t*>(abort_status), sig, ticket, s->expand_ticket_base);
-	s->expand_ticket_base += items + grid * uint32_t(kExpandWarps);
+		static_cast<uint32_t*>(status_dev), static_cast<const uint32_t*>(abort_status), sig);
 	ZN_CUDA(cudaGetLastError());
 	return ZN_OK;
 }
@@ -455,10 +452,11 @@ static int run_update(zn_scene* s, bool with_view) {
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
 	uint32_t* totals_next = s->chunk_total + size_t(s->frame_parity ^ 1u) * s->chunk_count;
 	if (with_view) s->frame_parity ^= 1u;
-	// Levels >= 1 and the emit kernel are launched with programmatic stream serialization: their
-	// prologue (and the first input-block load) overlaps the tail of the kernel before them; they
-	// call griddepcontrol.wait before touching anything that kernel wrote.  Level 0 is a normal
-	// launch, so a frame never overlaps the previous frame's emit.
+	// Every kernel of a frame is launched with programmatic stream serialization: its prologue (and
+	// the first input-block load) overlaps the tail of the kernel before it; it calls
+	// griddepcontrol.wait before touching anything that kernel wrote.  That includes level 0, whose
+	// start-up overlaps the previous frame's emit — unless an upload has written the input blocks in
+	// between (then the block load itself must wait, and level 0 is a normal launch).
 	cudaLaunchAttribute pdl;
 	pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	pdl.val.programmaticStreamSerializationAllowed = 1;
@@ -471,7 +469,7 @@ static int run_update(zn_scene* s, bool with_view) {
 		zn_level& lv = s->levels[l];
 		const uint32_t grid = std::min<uint32_t>(lv.tiles, uint32_t(s->max_ctas));
 		cfg.gridDim = dim3(grid);
-		cfg.numAttrs = (l == 0 || prof) ? 0 : 1;
+		cfg.numAttrs = ((l == 0 && s->inputs_touched) || prof) ? 0 : 1;
 		if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[l], ctx->stream));
 		uint32_t* ticket = s->level_ticket + l;   // one counter per level: PDL lets consecutive levels overlap
 		auto launch = [&](auto kernel) {
@@ -492,6 +490,7 @@ static int run_update(zn_scene* s, bool with_view) {
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
 	s->last_update_had_view = with_view;
 	s->world_valid = true;
+	s->inputs_touched = false;
 	return ZN_OK;
 }
 
@@ -560,10 +559,22 @@ int zn_scene_cull(zn_scene* s, const float view[16], const float proj[16], const
 	if (prof) ZN_CUDA(cudaEventRecord(s->cull_events[0], ctx->stream));
 	const uint32_t grid = std::min<uint32_t>(s->tile_count, uint32_t(s->max_ctas_cull));
 	uint32_t* ticket = s->level_ticket + s->levels.size();
-	scene_cull_kernel<<<grid, kTile, kCullSmem, ctx->stream>>>(s->tm_world_all, *tm_mvp, fc, s->blocks, s->tile_first_entity, s->tile_count,
-	                                                          s->entity_count, rec, record_header_words(s->chunk_count), totals, ticket,
-	                                                          s->cull_ticket_base);
-	ZN_CUDA(cudaGetLastError());
+	{
+		// programmatic launch behind the update (or the previous pass's emit): the prologue and the first AABB load overlap its tail
+		cudaLaunchAttribute pdl;
+		pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		pdl.val.programmaticStreamSerializationAllowed = 1;
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(grid);
+		cfg.blockDim = dim3(kTile);
+		cfg.dynamicSmemBytes = kCullSmem;
+		cfg.stream = ctx->stream;
+		cfg.attrs = &pdl;
+		cfg.numAttrs = (prof || s->inputs_touched) ? 0 : 1;
+		ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_cull_kernel, s->tm_world_all, *tm_mvp, fc, (const uint32_t*)s->blocks,
+		                           (const uint32_t*)s->tile_first_entity, s->tile_count, s->entity_count, rec,
+		                           record_header_words(s->chunk_count), totals, ticket, s->cull_ticket_base));
+	}
 	s->cull_ticket_base += s->tile_count + grid;
 	if (prof) ZN_CUDA(cudaEventRecord(s->cull_events[1], ctx->stream));
 	const int rc = launch_emit(s, rec, totals, totals_next, visible, visible_count, 0u, !prof);
@@ -576,12 +587,11 @@ int zn_scene_set_ticket_origin(zn_scene* s, uint32_t origin) {
 	ZN_REQUIRE(s, "zn_scene_set_ticket_origin: scene is NULL");
 	ZN_CUDA(cudaSetDevice(s->ctx->device));
 	ZN_CUDA(cudaStreamSynchronize(s->ctx->stream));
-	std::vector<uint32_t> init(s->levels.size() + 2, origin);
+	std::vector<uint32_t> init(s->levels.size() + 1, origin);
 	ZN_CUDA(cudaMemcpyAsync(s->level_ticket, init.data(), init.size() * 4, cudaMemcpyHostToDevice, s->ctx->stream));
 	ZN_CUDA(cudaStreamSynchronize(s->ctx->stream));
 	for (zn_level& lv : s->levels) lv.ticket_base = origin;
 	s->cull_ticket_base = origin;
-	s->expand_ticket_base = origin;
 	return ZN_OK;
 }
 
@@ -821,6 +831,7 @@ int zn_scene_frame_host_submit(zn_scene* s, const zn_frame_host_io* io) {
 		auto at = [&](int a) { return src[a] ? reinterpret_cast<const uint32_t*>(p->staging[k] + a * E * 12) : nullptr; };
 		repack_frame_kernel<<<(n_in + 255) / 256, 256, 0, ctx->stream>>>(at(0), at(1), at(2), io->first, n_in, s->blocks, lv);
 		ZN_CUDA(cudaGetLastError());
+		s->inputs_touched = true;
 	}
 	ZN_CUDA(cudaEventRecord(p->repacked[k], ctx->stream));
 	uint32_t* keep_vis = s->visible;

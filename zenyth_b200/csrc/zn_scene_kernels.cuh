@@ -121,8 +121,10 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 	const int warp = t >> 5;
 
 	// thread 0 is the TMA issuer: loads of tile `tl` into the (single) input stage.  `first_tile`:
-	// the input block does not depend on the previous level's kernel but the parent matrices do,
-	// so under programmatic dependent launch only the second copy waits for it.
+	// the input block does not depend on the kernel before this one on the stream (the previous
+	// level, or — for level 0 — the previous frame's emit) but the parent matrices, the masks and
+	// the chunk totals do, so under programmatic dependent launch the first block load is issued
+	// before griddepcontrol.wait and everything else after it.
 	auto issue_loads = [&](uint32_t tl, bool first_tile) {
 		const uint32_t gt = tile_base + tl;
 		uint2 pr = make_uint2(0u, 0u);
@@ -137,7 +139,7 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 			bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, 9u * kTile * 4u, &s_full);
 			bulk_g2s(const_cast<uint32_t*>(in_blk) + 15 * kTile, blocks + size_t(gt) * kBlockWords + 15 * kTile, kTile * 4u, &s_full);
 		}
-		if (HAS_PARENT && first_tile) grid_dep_wait();
+		if (first_tile) grid_dep_wait();   // everything from here on is ordered behind the kernel before this one on the stream
 		if (staged) bulk_g2s(const_cast<float4*>(in_par), world_rd + size_t(pr.x) * 16, pr.y * 64u, &s_full);
 	};
 
@@ -283,13 +285,17 @@ scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_con
 	const int lane = t & 31;
 	const int warp = t >> 5;
 
-	auto issue_loads = [&](uint32_t gt, uint32_t slot) {
+	// `first_tile`: the AABB rows do not depend on the kernel before this one on the stream (the update
+	// that composed the world matrices), the world matrices do: under programmatic dependent launch
+	// only the second copy waits for it.
+	auto issue_loads = [&](uint32_t gt, uint32_t slot, bool first_tile) {
 		const uint32_t first = __ldg(tile_first_entity + gt);
 		const uint32_t next = (gt + 1 < tiles) ? __ldg(tile_first_entity + gt + 1) : entity_count;
 		s_meta[slot] = make_uint2(first, next - first);
 		mbar_arrive_expect_tx(&s_full, kTile * 64u + kAabbBytes);
-		tensor_load_2d(const_cast<float4*>(in_world), &tm_world, 0, int32_t(first), &s_full);
 		bulk_g2s(const_cast<float*>(in_aabb), blocks + size_t(gt) * kBlockWords + 9 * kTile, kAabbBytes, &s_full);
+		if (first_tile) grid_dep_wait();
+		tensor_load_2d(const_cast<float4*>(in_world), &tm_world, 0, int32_t(first), &s_full);
 	};
 
 	if (t == 0) {
@@ -300,7 +306,7 @@ scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_con
 		grid_dep_launch();
 		const uint32_t g0 = atomicAdd(ticket, 1u) - ticket_base;
 		s_tile[0] = g0;
-		if (g0 < tiles) issue_loads(g0, 0);
+		if (g0 < tiles) issue_loads(g0, 0, true);
 	}
 	__syncthreads();
 
@@ -320,7 +326,7 @@ scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_con
 		if (t == 0) {
 			const uint32_t next = atomicAdd(ticket, 1u) - ticket_base;
 			s_tile[(n + 1u) & 1u] = next;
-			if (next < tiles) issue_loads(next, (n + 1u) & 1u);
+			if (next < tiles) issue_loads(next, (n + 1u) & 1u, false);
 		}
 		Affine w;
 		w.m[0][0] = c0.x; w.m[1][0] = c0.y; w.m[2][0] = c0.z;
@@ -436,6 +442,11 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 	__shared__ uint32_t s_base, s_total;
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
+	// thread t owns mask word t of the chunk: tile chunk*32 + t/8, word t%8.  Loaded up front, together with
+	// the totals (one round of loads instead of two; a full or empty chunk simply does not use it).
+	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
+	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (t & 7)) : 0u;
+	const uint32_t ctot = __ldcg(totals + chunk);
 	uint32_t acc = 0;
 	for (uint32_t j = t; j < chunk; j += 256) acc += __ldcg(totals + j);
 	acc = __reduce_add_sync(0xffffffffu, acc);
@@ -445,7 +456,6 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 	// the chunk total (accumulated by the level kernels) says so before a single mask word is read:
 	// the header is then known in closed form and the list segment is one run of 8192 indices.
 	// (Chunks whose masks this kernel must push to peers take the general path: it loads them.)
-	const uint32_t ctot = __ldcg(totals + chunk);
 	const bool pushes_masks = record_out.n > 1 && chunk * kChunkTiles < remote_tiles_below;
 	if ((ctot == 0u || ctot == uint32_t(kChunkTiles * kTile)) && !pushes_masks) {
 		__syncthreads();
@@ -470,9 +480,6 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 		return ctot;
 	}
 
-	// thread t owns mask word t of the chunk: tile chunk*32 + t/8, word t%8
-	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
-	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (t & 7)) : 0u;
 	// Masks of the SMALL leading levels reach the peers from here (coalesced, one kernel boundary)
 	// instead of from their level kernels, whose few microseconds would each end on an NVLink round
 	// trip; the big levels push their own masks tile by tile while they run.
@@ -544,6 +551,9 @@ emit_visible_kernel(const __grid_constant__ RecordTargets rec, const uint32_t* _
                     uint32_t index_base, uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count, uint32_t remote_tiles_below) {
 	const uint32_t chunk = blockIdx.x;
 	grid_dep_wait();   // masks and totals of every level are complete and visible
+	// The next frame's first kernel (level 0, or a cull pass) may start its prologue and first input
+	// load now; it calls griddepcontrol.wait itself before it writes a mask or touches a chunk total.
+	grid_dep_launch();
 	// rec.ptr[0] is this rank's own record (the masks are read from it); the header goes to all targets
 	emit_chunk(chunk_total, rec.ptr[0] + record_header_words(chunks), tile_first_entity, tiles, chunks, chunk, index_base, visible, visible_count, rec,
 	           remote_tiles_below);
@@ -575,135 +585,131 @@ __global__ void wait_flags_kernel(const uint32_t* __restrict__ flags, uint32_t f
 struct ExpandBases {
 	uint32_t base[64];
 };
-constexpr int kExpandWarps = 8;   // warps per CTA of the persistent expansion grid
+constexpr int kExpandWarps = 8;    // warps per CTA of the expansion grid, one chunk (8192 entities) per warp
 
 // A record already carries every offset its owner computed (chunk bases, group offsets), so a WARP
-// is autonomous: it draws one (record, chunk) item at a time from a ticket counter, reads the
-// chunk's ten header words, and then
-//   - skips an empty chunk or 4-tile group,
-//   - writes a full group as one run of 1024 consecutive indices,
-//   - walks the masks only of mixed groups (all 256 mask words of a mixed chunk are fetched with
-//     one round of coalesced loads before the first group is scattered).
-// The grid is persistent (as many CTAs as fit, no CTA is spent on an empty chunk) and no block
-// barrier or shared-memory reduction is involved.
+// is autonomous — no block barrier, no shared-memory reduction, no ticket counter.  It owns one
+// chunk (eight 4-tile groups) and issues EVERYTHING it may need in one round of loads before it
+// looks at any of it: the chunk's base and end, its eight group offsets, the chunk's 256 mask words
+// (8 per lane, coalesced; speculative: 1 KiB of L2 traffic per chunk, 2 MB per record) and the
+// tiles' first entity indices.  Then an empty chunk exits; of a non-empty one the full groups are
+// written as runs of 1024 consecutive indices straight from the header and the mixed groups are
+// scanned and scattered with the unrolled, branch-light walk of scatter_warp_words.
+// What bounds this kernel is latency times waves, not bytes: measured on the way here (7 records of
+// the 16.7M-entity scene, camera inside, f = 0.21: 70% of the chunks empty, 14% of the groups mixed
+// with 27 of their 32 words non-zero):
+//   one CTA per chunk, one group per warp: 115k warps = 12 waves, each at least the two or three
+//   dependent load rounds an EMPTY group needs before it can exit                     37 us
+//   the same with 32-warp CTAs and a single load round (still 12 waves)               51 us
+//   persistent warps drawing chunks from one ticket counter (same-address atomics: ~4 ns each)   67 us
+//   one warp per run of 32 groups walked one after the other (a lone warp retires a dependent
+//   instruction every ~10 cycles)                                                    117 us
+//   one warp per 4 groups, looping over non-zero words only (serial ffs/shfl chain)   52 us
+// One warp per chunk is 14k warps — a wave and a half — and an empty chunk costs its warp one load.
 //
-// Signalled form (flags != nullptr): a warp waits — lane 0, ld.acquire.sys, bounded — for the flag
-// of a record's owner the first time it draws an item of that record.  If the flag does not arrive
-// within the timeout the record is NOT expanded: 1 + r goes to *status (first failure wins),
-// counts[r] becomes 0 and every later item of that record is dropped, so a half-written record
-// never reaches the scatter.  `abort_status` (plain form after zn_scene_wait_flags): a non-zero word
-// there means that wait failed; nothing is expanded and all counts are zeroed.
+// Signalled form (flags != nullptr): lane 0 waits — ld.acquire.sys, bounded — for the flag of the
+// record's owner.  If the flag does not arrive within the timeout the record is NOT expanded: 1 + r
+// goes to *status (first failure wins), counts[r] becomes 0, so a half-written record never reaches
+// the scatter.  `abort_status` (plain form after zn_scene_wait_flags): a non-zero word there means
+// that wait failed; nothing is expanded and all counts are zeroed.
 __global__ void __launch_bounds__(kExpandWarps * 32)
 expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
                       uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, uint32_t record_count, int skip, int skip_count,
                       uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ counts,
                       const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t expected, uint32_t records_per_flag,
                       uint64_t timeout_ns, uint32_t* __restrict__ status, const uint32_t* __restrict__ abort_status,
-                      const __grid_constant__ SignalTargets sig, uint32_t* __restrict__ ticket, uint32_t ticket_base) {
-	__shared__ __align__(16) uint32_t s_word[kExpandWarps][32];
+                      const __grid_constant__ SignalTargets sig) {
+	__shared__ __align__(16) uint32_t s_word[kExpandWarps][256];     // the chunk's mask words, group-major
 	__shared__ __align__(16) uint32_t s_off[kExpandWarps][32];
 	__shared__ uint32_t s_first[kExpandWarps][4];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (sig.n > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+	if (sig.n > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
 		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank
 		raise_flags(sig);
 	}
-	const uint32_t live = record_count - uint32_t(skip_count);       // records this launch expands
-	const uint32_t items = live * chunks;
+	uint32_t r = blockIdx.y;                                         // one grid row per expanded record
+	if (int(r) >= skip) r += uint32_t(skip_count);
+	if (r >= record_count) return;                                   // every record skipped: this launch only signals
+	const uint32_t chunk = blockIdx.x * kExpandWarps + warp;
+	if (chunk >= chunks) return;
 	if (abort_status && __ldcg(abort_status) != 0u) {
-		if (blockIdx.x == 0 && threadIdx.x < record_count && !(int(threadIdx.x) >= skip && int(threadIdx.x) < skip + skip_count)) counts[threadIdx.x] = 0u;
-		// keep the ticket counter where the host expects it after this launch (every item + one stop draw per warp)
-		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(ticket, items + gridDim.x * uint32_t(kExpandWarps));
+		if (chunk == 0 && lane == 0) counts[r] = 0u;
 		return;
 	}
-	const uint32_t lt = (1u << lane) - 1u;
-	uint64_t ready = 0, failed = 0;                                  // per-warp memo of the records' flags (warp-uniform)
-	for (;;) {
-		uint32_t item = 0;
-		if (lane == 0) item = atomicAdd(ticket, 1u) - ticket_base;
-		item = __shfl_sync(0xffffffffu, item, 0);
-		if (item >= items) break;
-		// chunk-major: consecutive tickets belong to different records, so warps that must wait for one
-		// owner's flag leave the other records' chunks to the rest of the grid
-		const uint32_t chunk = item / live;
-		uint32_t r = item - chunk * live;
-		if (int(r) >= skip) r += uint32_t(skip_count);
-		if (flags && !((ready >> r) & 1ull)) {
-			if ((failed >> r) & 1ull) {
-				if (chunk == 0 && lane == 0) counts[r] = 0u;
-				continue;
-			}
-			uint32_t ok = 1u;
-			if (lane == 0) {
-				const uint32_t* f = flags + size_t(r / records_per_flag) * flag_stride;
-				const uint64_t t0 = global_timer_ns();
-				while (int32_t(ld_acquire_sys(f) - expected) < 0) {
-					// someone else already gave up on this record, or the time is up
-					if (*reinterpret_cast<volatile uint32_t*>(status) == 1u + r || global_timer_ns() - t0 > timeout_ns) {
-						atomicCAS(status, 0u, 1u + r);
-						ok = 0u;
-						break;
-					}
-					__nanosleep(200);
+	if (flags) {
+		uint32_t ok = 1u;
+		if (lane == 0) {
+			const uint32_t* f = flags + size_t(r / records_per_flag) * flag_stride;
+			const uint64_t t0 = global_timer_ns();
+			while (int32_t(ld_acquire_sys(f) - expected) < 0) {
+				// someone else already gave up on this record, or the time is up
+				if (*reinterpret_cast<volatile uint32_t*>(status) == 1u + r || global_timer_ns() - t0 > timeout_ns) {
+					atomicCAS(status, 0u, 1u + r);
+					ok = 0u;
+					break;
 				}
-			}
-			ok = __shfl_sync(0xffffffffu, ok, 0);     // also extends lane 0's acquire to the warp
-			if (!ok) {
-				failed |= 1ull << r;
-				if (chunk == 0 && lane == 0) counts[r] = 0u;
-				continue;
-			}
-			ready |= 1ull << r;
-		}
-		const uint32_t* rec = records + size_t(r) * record_stride;
-		const uint32_t* masks = rec + record_header_words(chunks);
-		uint32_t* visible = lists + size_t(r) * list_stride;
-		// header: lane 0 the chunk's base, lane 1 the next chunk's (or the total), lanes 8..15 the group offsets
-		uint32_t h = 0;
-		if (lane < 2) h = __ldcg(rec + chunk + lane);
-		else if (lane >= 8 && lane < 16) h = __ldcg(rec + chunks + 1u + chunk * 8u + (lane - 8));
-		const uint32_t chunk_base = __shfl_sync(0xffffffffu, h, 0);
-		const uint32_t chunk_count = __shfl_sync(0xffffffffu, h, 1) - chunk_base;
-		if (chunk == 0 && lane == 0) counts[r] = __ldcg(rec + chunks);
-		if (chunk_count == 0u || chunk_count > uint32_t(kChunkTiles * kTile)) continue;   // empty (or not a record)
-		const bool mixed_chunk = chunk_count != uint32_t(kChunkTiles * kTile);
-		uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-		if (mixed_chunk) {
-#pragma unroll
-			for (int g = 0; g < 8; ++g) {
-				const uint32_t tile = (chunk * 8u + g) * 4u + (lane >> 3);
-				w[g] = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
+				__nanosleep(200);
 			}
 		}
-#pragma unroll
-		for (int g = 0; g < 8; ++g) {
-			const uint32_t group = chunk * 8u + g;
-			if (group * 4u >= tiles) break;
-			const uint32_t group_off = __shfl_sync(0xffffffffu, h, 8 + g);
-			const uint32_t group_end = (g < 7) ? __shfl_sync(0xffffffffu, h, 9 + g) : chunk_count;
-			const uint32_t group_count = group_end - group_off;
-			if (group_count == 0u || group_count > 4u * kTile) continue;
-			const uint32_t base = chunk_base + group_off;
-			if (group_count == 4u * kTile) {
-				store_run_1024(visible + base, __ldg(tile_first_entity + group * 4u) + bases.base[r], lane);
-				continue;
-			}
-			const uint32_t tile = group * 4u + (lane >> 3);
-			const uint32_t word = w[g];
-			const uint32_t cnt = __popc(word);
-			uint32_t incl = cnt;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-				if (lane >= d) incl += y;
-			}
-			__syncwarp();
-			s_word[warp][lane] = word;
-			s_off[warp][lane] = base + incl - cnt;
-			if ((lane & 7) == 0) s_first[warp][lane >> 3] = (tile < tiles) ? __ldg(tile_first_entity + tile) + bases.base[r] : 0u;
-			__syncwarp();
-			scatter_warp_words(reinterpret_cast<const uint4*>(s_word[warp]), reinterpret_cast<const uint4*>(s_off[warp]), s_first[warp], lane, lt, visible);
+		ok = __shfl_sync(0xffffffffu, ok, 0);     // also extends lane 0's acquire to the warp
+		if (!ok) {
+			if (chunk == 0 && lane == 0) counts[r] = 0u;
+			return;
 		}
+	}
+	const uint32_t* rec = records + size_t(r) * record_stride;
+	const uint32_t* masks = rec + record_header_words(chunks);
+	uint32_t* visible = lists + size_t(r) * list_stride;
+	const uint32_t index_base = bases.base[r];
+	// ---- one round of loads ---------------------------------------------------------------------------
+	// header: lane 0 the chunk's base, lane 1 the next chunk's (entry `chunks` is the total), lanes 8..15 the group offsets
+	uint32_t h = 0u;
+	if (lane < 2) h = __ldcg(rec + chunk + lane);
+	else if (lane >= 8 && lane < 16) h = __ldcg(rec + chunks + 1u + chunk * 8u + (lane - 8));
+	uint32_t w[8];
+#pragma unroll
+	for (int g = 0; g < 8; ++g) {                                    // word `lane` of group g: tile (chunk*8+g)*4 + lane/8, word lane%8
+		const uint32_t tile = (chunk * 8u + g) * 4u + (lane >> 3);
+		w[g] = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
+	}
+	const uint32_t my_tile = chunk * kChunkTiles + lane;             // lane l: tile l of the chunk's 32
+	const uint32_t tf = (my_tile < tiles) ? __ldg(tile_first_entity + my_tile) + index_base : 0u;
+	if (chunk == 0 && lane == 0) counts[r] = __ldcg(rec + chunks);
+	const uint32_t chunk_base = __shfl_sync(0xffffffffu, h, 0);
+	const uint32_t chunk_count = __shfl_sync(0xffffffffu, h, 1) - chunk_base;
+	if (chunk_count == 0u || chunk_count > uint32_t(kChunkTiles * kTile)) return;   // empty (or not a record)
+	const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+	for (int g = 0; g < 8; ++g) s_word[warp][g * 32 + lane] = w[g];
+	__syncwarp();
+	// NOT unrolled: eight inlined copies of the scatter are 27k instructions, far beyond the instruction
+	// cache (measured: ~3 us per mixed group instead of ~0.5)
+#pragma unroll 1
+	for (int g = 0; g < 8; ++g) {
+		if ((chunk * 8u + g) * 4u >= tiles) break;                   // warp-uniform
+		const uint32_t group_off = __shfl_sync(0xffffffffu, h, 8 + g);
+		const uint32_t group_end = (g < 7) ? __shfl_sync(0xffffffffu, h, 9 + g) : chunk_count;
+		const uint32_t group_count = group_end - group_off;
+		if (group_count == 0u || group_count > 4u * kTile) continue;
+		const uint32_t base = chunk_base + group_off;
+		if (group_count == 4u * kTile) {
+			store_run_1024(visible + base, __shfl_sync(0xffffffffu, tf, g * 4), lane);
+			continue;
+		}
+		const uint32_t word = s_word[warp][g * 32 + lane];
+		const uint32_t cnt = __popc(word);
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= d) incl += y;
+		}
+		const uint32_t tfirst = __shfl_sync(0xffffffffu, tf, g * 4 + (lane & 3));   // lanes 0..3 fetch the group's four tiles
+		__syncwarp();
+		s_off[warp][lane] = base + incl - cnt;
+		if (lane < 4) s_first[warp][lane] = tfirst;
+		__syncwarp();
+		scatter_warp_words(reinterpret_cast<const uint4*>(s_word[warp] + g * 32), reinterpret_cast<const uint4*>(s_off[warp]), s_first[warp], lane, lt, visible);
 	}
 }
 

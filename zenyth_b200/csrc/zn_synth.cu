@@ -81,6 +81,7 @@ int zn_scene_fill_synthetic(zn_scene* s, uint32_t seed, uint32_t fanout, float a
 		                                                               prev_off, prev_size, fanout, l == 0 ? 1 : 0, aabb_center_range);
 	}
 	s->ranges_dirty = true;
+	s->inputs_touched = true;
 	ZN_CUDA(cudaGetLastError());
 	ZN_CUDA(cudaStreamSynchronize(s->ctx->stream));
 	return ZN_OK;

@@ -249,6 +249,13 @@ class PeerRecordExchange:
     def expand(self, scene, frame: int, index_bases=None) -> bool:
         """Derive every PEER's list of `frame` into lists[frame % 2] (asynchronous); False if the frame
         was never issued or is already expanded."""
+        if frame < 0 and self.issued == 0 and self.expanded < 0 and self.signal == "flags":
+            # frame 0 is updated, nothing to expand yet: a signal-only launch (every record skipped) raises its flags now
+            scene.ExpandVisibleSignalled(self.base, self.total_records, self.record_words, self._list_ptr(0), self.capacity,
+                                         self._count_ptr(0), self.base + self.flags_offset, FLAG_STRIDE_WORDS, 0,
+                                         self.status.data_ptr(), skip_index=0, skip_count=self.total_records,
+                                         records_per_flag=self.records_per_rank, timeout_ms=self.timeout_ms)
+            return False
         if frame < 0 or frame > self.issued or frame <= self.expanded:
             return False
         assert frame == self.expanded + 1, "frames are expanded in order"
