@@ -515,9 +515,9 @@ def make_exchange(rig: Rig, mode: str, words: int, E: int, records_per_rank: int
             note, mode = f"--exchange {mode} unavailable ({e}); ran --exchange records", "records"
     if mode == "records":
         from zenyth_b200.distributed import RecordExchange
-        return RecordExchange(words, E, rig.world_size, rig.dev, torch.int32, slots=2, records_per_rank=records_per_rank), mode, note
+        return RecordExchange(words, E, rig.world_size, rig.dev, torch.int32, slots=2, records_per_rank=records_per_rank, ctx=rig.ctx), mode, note
     from zenyth_b200.distributed import VisibleExchange
-    return VisibleExchange(E, rig.world_size, rig.dev, torch.int32, slots=2), "lists", note
+    return VisibleExchange(E, rig.world_size, rig.dev, torch.int32, slots=2, ctx=rig.ctx), "lists", note
 
 
 COLLECTIVE_NOTES = {

@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import zenyth_b200 as zn  # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 7
+EYE_Z = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
 torch.cuda.set_stream(stream)
@@ -18,7 +19,7 @@ sizes = [7 * 8 ** l for l in range(8)]
 E = sum(sizes)
 sc = zn.Scene(ctx, E, np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32))
 sc.FillSynthetic(0x5A454E59 + 3, 8, 0.0)
-sc.SetCamera(zn.Camera(zn.CameraDesc(eye=(0.0, 0.0, 0.0), center=(0.0, 0.0, -1.0))))
+sc.SetCamera(zn.Camera(zn.CameraDesc(eye=(0.0, 0.0, EYE_Z), center=(0.0, 0.0, EYE_Z - 1.0))))
 words = sc.DeviceBuffers().visibility_record_words
 recs = torch.zeros(R * words, dtype=torch.int32, device=dev)
 sc.BindVisibilityRecord(recs.data_ptr())

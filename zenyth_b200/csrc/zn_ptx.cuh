@@ -79,6 +79,20 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- per-thread asynchronous copies global -> shared (LDGSTS), 4 bytes each, completion by commit groups -----
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// A store that is PREDICATED, not branched around: nvcc turns `if (c) *p = v;` into a reconvergence
+// region (BSSY / BRA / BSYNC) per store, which serialises a run of independent conditional stores.
+__device__ __forceinline__ void st_global_if(uint32_t* p, uint32_t v, uint32_t cond) {
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(cond) : "memory");
+}
+
 // ---- cache-hinted global access ----------------------------------------------------------------
 __device__ __forceinline__ float ld_stream(const float* p) {
 	float v;

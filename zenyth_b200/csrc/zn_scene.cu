@@ -337,9 +337,9 @@ static int expand_visible(zn_scene* s, const char* who, const void* records_dev,
 		for (uint32_t* flag : s->peer_flags) sig.flag[sig.n++] = flag;
 		sig.value = s->signal_value;
 	}
-	// One warp per chunk, eight per CTA, one grid row per expanded record.
-	const dim3 grid((s->chunk_count + kExpandWarps - 1) / kExpandWarps, std::max<uint32_t>(1u, record_count - skip_count));
+	// One CTA per (record, chunk), one warp per 4-tile group.
 	if (record_count == skip_count && !flags_dev) return ZN_OK;     // nothing to expand and nothing to signal
+	const dim3 grid((s->chunk_count + kExpandChunks - 1) / kExpandChunks, std::max<uint32_t>(1u, record_count - skip_count));
 	expand_visible_kernel<<<grid, kExpandWarps * 32, 0, s->ctx->stream>>>(
 		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count,
 		skip_index, int(skip_count), static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),

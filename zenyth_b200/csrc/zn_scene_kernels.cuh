@@ -377,41 +377,25 @@ __host__ __device__ inline uint32_t record_header_words(uint32_t chunks) { retur
 
 // The scatter of one warp's 32 mask words (4 tiles), staged in shared memory as words w4[8] and
 // list offsets o4[8] (four per LDS.128, broadcast) with the tiles' first indices in first[4].
-// Lane l owns bit l of every word, so the stores of a word are one coalesced ascending run.  A
-// word is warp-uniform, so none of the branches diverge.  Visibility is spatially coherent: most
-// groups of four words are all-ones — 128 consecutive indices, written as one 16-byte store per
-// lane when the destination is 16-byte aligned — or all-zero.
+// Lane l owns bit l of every word, so the stores of a word are one coalesced ascending run.
+// STRAIGHT-LINE code: one predicated store per word and nothing else — no fast paths, no branches.
+// A warp that scatters alone is bound by the latency of its instruction stream, not by issue slots:
+// the earlier form with all-ones / all-zero fast paths compiled to a reconvergence region per word
+// (BSSY ... BSYNC, ~30 dependent instructions each) and took ~3 us per group; 32 independent
+// test-popc-add-store chains overlap freely.  (Full GROUPS never get here: the callers write them as
+// runs of 1024 indices straight from the counts.)
 __device__ __forceinline__ void scatter_warp_words(const uint4* __restrict__ w4, const uint4* __restrict__ o4,
                                                    const uint32_t* __restrict__ first, int lane, uint32_t lt,
                                                    uint32_t* __restrict__ visible) {
 #pragma unroll
 	for (int g = 0; g < 8; ++g) {   // words 4g..4g+3 belong to tile g/2 of this warp
 		const uint4 m = w4[g];
-		if ((m.x | m.y | m.z | m.w) == 0u) continue;
 		const uint4 o = o4[g];
-		const uint32_t f0 = first[g >> 1] + (g & 1) * 128;
-		if ((m.x & m.y & m.z & m.w) == 0xffffffffu) {
-			if ((reinterpret_cast<uintptr_t>(visible + o.x) & 15u) == 0u) {
-				const uint32_t v = f0 + lane * 4;
-				*reinterpret_cast<uint4*>(visible + o.x + lane * 4) = make_uint4(v, v + 1, v + 2, v + 3);
-			} else {
-				const uint32_t v = f0 + lane;
-				visible[o.x + lane] = v;
-				visible[o.x + 32 + lane] = v + 32;
-				visible[o.x + 64 + lane] = v + 64;
-				visible[o.x + 96 + lane] = v + 96;
-			}
-			continue;
-		}
-		const uint32_t f = f0 + lane;
-		auto put = [&](uint32_t mw, uint32_t off, uint32_t value) {
-			if (mw == 0xffffffffu) visible[off + lane] = value;
-			else if (mw != 0u && ((mw >> lane) & 1u)) visible[off + __popc(mw & lt)] = value;
-		};
-		put(m.x, o.x, f);
-		put(m.y, o.y, f + 32);
-		put(m.z, o.z, f + 64);
-		put(m.w, o.w, f + 96);
+		const uint32_t f = first[g >> 1] + (g & 1) * 128 + lane;
+		st_global_if(visible + o.x + __popc(m.x & lt), f, (m.x >> lane) & 1u);
+		st_global_if(visible + o.y + __popc(m.y & lt), f + 32, (m.y >> lane) & 1u);
+		st_global_if(visible + o.z + __popc(m.z & lt), f + 64, (m.z >> lane) & 1u);
+		st_global_if(visible + o.w + __popc(m.w & lt), f + 96, (m.w >> lane) & 1u);
 	}
 }
 
@@ -420,15 +404,22 @@ __device__ __forceinline__ void scatter_warp_words(const uint4* __restrict__ w4,
 // boundary: a level whose last tile is full ends where the next one begins), so neither the masks
 // nor a scan are needed — the counts in the record header already say "all of them".
 __device__ __forceinline__ void store_run_1024(uint32_t* __restrict__ out, uint32_t v0, int lane) {
-	if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0u) {
+	// `out` is only 4-byte aligned in general (a list position is a count of visible entities — at the
+	// bench's headline camera every group starts 2 words off a 16-byte boundary): peel `a` leading
+	// words so that the body leaves as 16-byte stores, 255 of them, and finish with the 4 - a trailing
+	// words.  (Falling back to 32-bit stores for unaligned runs cost a quarter of the write bandwidth.)
+	const uint32_t a = (4u - ((uint32_t(reinterpret_cast<uintptr_t>(out)) >> 2) & 3u)) & 3u;   // warp-uniform
+	uint32_t* body = out + a;
+	const uint32_t vb = v0 + a;
 #pragma unroll
-		for (int k = 0; k < 8; ++k) {
-			const uint32_t v = v0 + k * 128 + lane * 4;
-			*reinterpret_cast<uint4*>(out + k * 128 + lane * 4) = make_uint4(v, v + 1, v + 2, v + 3);
-		}
-	} else {
-#pragma unroll 8
-		for (int k = 0; k < 32; ++k) out[k * 32 + lane] = v0 + k * 32 + lane;
+	for (int k = 0; k < 8; ++k) {
+		const uint32_t i = uint32_t(k) * 32u + lane;           // 16-byte slot of the body
+		const uint32_t v = vb + i * 4u;
+		if (a == 0u || i < 255u) *reinterpret_cast<uint4*>(body + i * 4u) = make_uint4(v, v + 1, v + 2, v + 3);
+	}
+	if (a != 0u) {
+		if (uint32_t(lane) < a) out[lane] = v0 + lane;                                          // head
+		else if (uint32_t(lane) < 4u) out[1020u + lane] = v0 + 1020u + lane;                    // tail: words 1020+a .. 1023
 	}
 }
 
@@ -585,27 +576,37 @@ __global__ void wait_flags_kernel(const uint32_t* __restrict__ flags, uint32_t f
 struct ExpandBases {
 	uint32_t base[64];
 };
-constexpr int kExpandWarps = 8;    // warps per CTA of the expansion grid, one chunk (8192 entities) per warp
+constexpr int kExpandChunks = 1;   // chunks per CTA of the expansion grid (4, i.e. 32-warp CTAs, measured slower: 40 / 70 us)
+constexpr int kExpandWarps = 8 * kExpandChunks;   // one 4-tile group per warp
 
 // A record already carries every offset its owner computed (chunk bases, group offsets), so a WARP
-// is autonomous — no block barrier, no shared-memory reduction, no ticket counter.  It owns one
-// chunk (eight 4-tile groups) and issues EVERYTHING it may need in one round of loads before it
-// looks at any of it: the chunk's base and end, its eight group offsets, the chunk's 256 mask words
-// (8 per lane, coalesced; speculative: 1 KiB of L2 traffic per chunk, 2 MB per record) and the
-// tiles' first entity indices.  Then an empty chunk exits; of a non-empty one the full groups are
-// written as runs of 1024 consecutive indices straight from the header and the mixed groups are
-// scanned and scattered with the unrolled, branch-light walk of scatter_warp_words.
-// What bounds this kernel is latency times waves, not bytes: measured on the way here (7 records of
-// the 16.7M-entity scene, camera inside, f = 0.21: 70% of the chunks empty, 14% of the groups mixed
-// with 27 of their 32 words non-zero):
-//   one CTA per chunk, one group per warp: 115k warps = 12 waves, each at least the two or three
-//   dependent load rounds an EMPTY group needs before it can exit                     37 us
-//   the same with 32-warp CTAs and a single load round (still 12 waves)               51 us
-//   persistent warps drawing chunks from one ticket counter (same-address atomics: ~4 ns each)   67 us
-//   one warp per run of 32 groups walked one after the other (a lone warp retires a dependent
-//   instruction every ~10 cycles)                                                    117 us
-//   one warp per 4 groups, looping over non-zero words only (serial ffs/shfl chain)   52 us
-// One warp per chunk is 14k warps — a wave and a half — and an empty chunk costs its warp one load.
+// is autonomous — no block barrier, no shared-memory reduction.  One CTA per (record, chunk), one
+// 4-tile group (1024 entities) per warp.  A warp reads four header words (the chunk's base and end,
+// the group's offset and the next one — L1-cached, shared by the CTA's warps and its neighbours); an
+// empty group exits on them; a full group is written as one run of 1024 consecutive indices straight
+// from the header (16-byte stores whatever the run's alignment); only a mixed group fetches its 32
+// mask words, scans them and scatters with the straight-line scatter_warp_words.
+//
+// What was measured on the way here (7 records of the 16.7M-entity scene; camera inside, f = 0.21:
+// 70% of the chunks empty, 14% of the groups mixed with 27 of their 32 words non-zero, a plain fill
+// of the same bytes takes 16.5 us / headline camera, f = 0.86, nearly every group full or empty,
+// fill 56 us).  Round 1's kernel — this structure, but header -> offsets -> masks as three dependent
+// load rounds, 32-bit stores for unaligned runs and a scatter with all-ones / all-zero fast paths
+// that compiled to a reconvergence region per word (a lone warp retires a dependent instruction
+// every ~10 cycles: ~3 us per mixed group) —                                              37 / 64 us
+//   persistent warps drawing chunks from one GLOBAL ticket counter (same-address atomics, ~4 ns each)  67 / 78
+//   one warp per chunk, eight inlined copies of the scatter (27k instructions: instruction cache)     65 / 77
+//   one warp per chunk, loop not unrolled, straight-line predicated scatter (~1.1 us per group)        36 / 78
+//   eight chunks per CTA, scouted, non-empty groups shared through a shared-memory work list           37 / 80
+//   persistent warps, static stride over the groups, 1 or 8 items in flight per warp (LDGSTS ring)     39-41 / 80-84
+//   this structure, single speculative load round, L2-only (.cg) loads                                  39 / 68
+//   this structure, L1-cached header loads, masks fetched by mixed groups only (what is below)         36 / 64
+// None of the coarser-grained or persistent forms beat a wide grid of small, short-lived warps: the
+// kernel is bound by how many independent 4 KiB store runs and scatters are in flight, and at f = 0.86
+// ncu shows the persistent form at 42% issue utilisation and 54% DRAM throughput with MIO / LSU
+// throttle stalls (profiles/r02_expand_persistent_ncu.csv).  A single record takes 9 us (round 1: 11),
+// three take 16.5 us (round 1: 20): the per-record cost above that is the stream of 16k mostly empty
+// warps per record through the SMs.
 //
 // Signalled form (flags != nullptr): lane 0 waits — ld.acquire.sys, bounded — for the flag of the
 // record's owner.  If the flag does not arrive within the timeout the record is NOT expanded: 1 + r
@@ -619,7 +620,7 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
                       const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t expected, uint32_t records_per_flag,
                       uint64_t timeout_ns, uint32_t* __restrict__ status, const uint32_t* __restrict__ abort_status,
                       const __grid_constant__ SignalTargets sig) {
-	__shared__ __align__(16) uint32_t s_word[kExpandWarps][256];     // the chunk's mask words, group-major
+	__shared__ __align__(16) uint32_t s_word[kExpandWarps][32];
 	__shared__ __align__(16) uint32_t s_off[kExpandWarps][32];
 	__shared__ uint32_t s_first[kExpandWarps][4];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -630,10 +631,12 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 	uint32_t r = blockIdx.y;                                         // one grid row per expanded record
 	if (int(r) >= skip) r += uint32_t(skip_count);
 	if (r >= record_count) return;                                   // every record skipped: this launch only signals
-	const uint32_t chunk = blockIdx.x * kExpandWarps + warp;
+	const uint32_t chunk = blockIdx.x * kExpandChunks + (warp >> 3);
 	if (chunk >= chunks) return;
+	const uint32_t group = chunk * 8u + (warp & 7);
+	const bool first = group == 0u;                                  // the warp that also delivers the record's count
 	if (abort_status && __ldcg(abort_status) != 0u) {
-		if (chunk == 0 && lane == 0) counts[r] = 0u;
+		if (first && lane == 0) counts[r] = 0u;
 		return;
 	}
 	if (flags) {
@@ -653,64 +656,52 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 		}
 		ok = __shfl_sync(0xffffffffu, ok, 0);     // also extends lane 0's acquire to the warp
 		if (!ok) {
-			if (chunk == 0 && lane == 0) counts[r] = 0u;
+			if (first && lane == 0) counts[r] = 0u;
 			return;
 		}
 	}
 	const uint32_t* rec = records + size_t(r) * record_stride;
-	const uint32_t* masks = rec + record_header_words(chunks);
 	uint32_t* visible = lists + size_t(r) * list_stride;
-	const uint32_t index_base = bases.base[r];
-	// ---- one round of loads ---------------------------------------------------------------------------
-	// header: lane 0 the chunk's base, lane 1 the next chunk's (entry `chunks` is the total), lanes 8..15 the group offsets
+	// ---- header ----------------------------------------------------------------------------------------------
+	// lane 0 the chunk's base, lane 1 the next chunk's (entry `chunks` is the total), lane 2 this group's offset,
+	// lane 3 the next group's (the header holds 8 offsets for every chunk), lane 4 the record's total (first warp only).
+	// Plain (L1-cached) loads: the eight warps of a CTA and the next CTAs on this SM read the same few lines, so
+	// most EMPTY groups — 70% of them at f = 0.21 — learn that they are empty at L1 latency and leave.  The
+	// record is complete before these loads by the memory model itself: it was written by kernels that
+	// finished before this one started (plain form), or is read after the acquire of its owner's flag above.
 	uint32_t h = 0u;
-	if (lane < 2) h = __ldcg(rec + chunk + lane);
-	else if (lane >= 8 && lane < 16) h = __ldcg(rec + chunks + 1u + chunk * 8u + (lane - 8));
-	uint32_t w[8];
-#pragma unroll
-	for (int g = 0; g < 8; ++g) {                                    // word `lane` of group g: tile (chunk*8+g)*4 + lane/8, word lane%8
-		const uint32_t tile = (chunk * 8u + g) * 4u + (lane >> 3);
-		w[g] = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
-	}
-	const uint32_t my_tile = chunk * kChunkTiles + lane;             // lane l: tile l of the chunk's 32
-	const uint32_t tf = (my_tile < tiles) ? __ldg(tile_first_entity + my_tile) + index_base : 0u;
-	if (chunk == 0 && lane == 0) counts[r] = __ldcg(rec + chunks);
+	if (lane < 2) h = rec[chunk + lane];
+	else if (lane < 4 && group + (lane - 2) < chunks * 8u) h = rec[chunks + 1u + group + (lane - 2)];
+	else if (lane == 4 && first) h = rec[chunks];
+	if (first && lane == 4) counts[r] = h;
+	if (group * 4u >= tiles) return;
 	const uint32_t chunk_base = __shfl_sync(0xffffffffu, h, 0);
 	const uint32_t chunk_count = __shfl_sync(0xffffffffu, h, 1) - chunk_base;
-	if (chunk_count == 0u || chunk_count > uint32_t(kChunkTiles * kTile)) return;   // empty (or not a record)
-	const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-	for (int g = 0; g < 8; ++g) s_word[warp][g * 32 + lane] = w[g];
-	__syncwarp();
-	// NOT unrolled: eight inlined copies of the scatter are 27k instructions, far beyond the instruction
-	// cache (measured: ~3 us per mixed group instead of ~0.5)
-#pragma unroll 1
-	for (int g = 0; g < 8; ++g) {
-		if ((chunk * 8u + g) * 4u >= tiles) break;                   // warp-uniform
-		const uint32_t group_off = __shfl_sync(0xffffffffu, h, 8 + g);
-		const uint32_t group_end = (g < 7) ? __shfl_sync(0xffffffffu, h, 9 + g) : chunk_count;
-		const uint32_t group_count = group_end - group_off;
-		if (group_count == 0u || group_count > 4u * kTile) continue;
-		const uint32_t base = chunk_base + group_off;
-		if (group_count == 4u * kTile) {
-			store_run_1024(visible + base, __shfl_sync(0xffffffffu, tf, g * 4), lane);
-			continue;
-		}
-		const uint32_t word = s_word[warp][g * 32 + lane];
-		const uint32_t cnt = __popc(word);
-		uint32_t incl = cnt;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-			if (lane >= d) incl += y;
-		}
-		const uint32_t tfirst = __shfl_sync(0xffffffffu, tf, g * 4 + (lane & 3));   // lanes 0..3 fetch the group's four tiles
-		__syncwarp();
-		s_off[warp][lane] = base + incl - cnt;
-		if (lane < 4) s_first[warp][lane] = tfirst;
-		__syncwarp();
-		scatter_warp_words(reinterpret_cast<const uint4*>(s_word[warp] + g * 32), reinterpret_cast<const uint4*>(s_off[warp]), s_first[warp], lane, lt, visible);
+	const uint32_t group_off = __shfl_sync(0xffffffffu, h, 2);
+	const uint32_t group_end = ((warp & 7) < 7) ? __shfl_sync(0xffffffffu, h, 3) : chunk_count;
+	const uint32_t group_count = group_end - group_off;
+	if (chunk_count > uint32_t(kChunkTiles * kTile) || group_count == 0u || group_count > 4u * kTile) return;   // empty (or not a record)
+	const uint32_t base = chunk_base + group_off;
+	const uint32_t tile = group * 4u + (lane >> 3);
+	const uint32_t tfirst = (tile < tiles) ? __ldg(tile_first_entity + tile) + bases.base[r] : 0u;
+	if (group_count == 4u * kTile) {
+		store_run_1024(visible + base, __shfl_sync(0xffffffffu, tfirst, 0), lane);
+		return;
 	}
+	const uint32_t word = (tile < tiles) ? rec[record_header_words(chunks) + size_t(tile) * kWarpsPerTile + (lane & 7)] : 0u;
+	const uint32_t cnt = __popc(word);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += y;
+	}
+	s_word[warp][lane] = word;
+	s_off[warp][lane] = base + incl - cnt;
+	if ((lane & 7) == 0) s_first[warp][lane >> 3] = tfirst;
+	__syncwarp();
+	scatter_warp_words(reinterpret_cast<const uint4*>(s_word[warp]), reinterpret_cast<const uint4*>(s_off[warp]), s_first[warp], lane,
+	                   (1u << lane) - 1u, visible);
 }
 
 // Visible list -> what a draw submission consumes: the MVP matrices of the

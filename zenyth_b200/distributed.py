@@ -1,6 +1,14 @@
 """Multi-GPU plumbing for the one exchange the path has: after every rank has
 updated the scenes it owns, all-gather the compacted visible COUNTS, then the index LISTS.
 
+STREAM CONTRACT of the NCCL-based classes here (VisibleGather / VisibleExchange / RecordExchange):
+torch orders a collective against torch's CURRENT stream only.  A GpuContext runs Scene.Update on
+its own non-blocking stream unless it was given torch's (`GpuContext(device, stream=torch.cuda.
+current_stream().cuda_stream)`, as bench.py and the tests do) — otherwise the all-gather can read a
+list or record the update has not written yet, silently.  Pass `ctx=` to the exchange constructors and
+every launch() checks that the two streams are the same.  (The product path for N > 1,
+zenyth_b200.peer_exchange.PeerExchange over zn_exchange_*, involves no torch stream at all.)
+
 One process per GPU; `torch.distributed` provides the collective (NCCL over NVLink/NVSwitch on the
 GPU box, gloo in the CPU tests).  Scenes are independent, so nothing else ever crosses GPUs:
 matrices stay where they were computed.  Everything here is host logic over torch tensors; it
@@ -20,6 +28,17 @@ def _check_value(rc: int) -> None:
     """Host-side argument errors of the C layer surface as ValueError here."""
     if rc != 0:
         raise ValueError(_lib().zn_last_error().decode("utf-8", "replace"))
+
+
+def check_same_stream(ctx) -> None:
+    """Raise if `ctx` (a GpuContext) enqueues its kernels on a stream other than torch's current one."""
+    if ctx is None:
+        return
+    import torch
+    mine, torchs = ctx.GetStream(), torch.cuda.current_stream().cuda_stream
+    if mine != torchs:
+        raise RuntimeError(f"the scene's context runs on stream {mine:#x} but torch's current stream is {torchs:#x}: a collective "
+                           "enqueued now would not be ordered after Scene.Update (create the context with stream=torch's stream)")
 
 
 def shard_scenes(num_scenes: int, world_size: int, rank: int) -> List[int]:
@@ -199,8 +218,9 @@ class VisibleExchange:
     a list outgrew the guess the frame is re-gathered synchronously, so results are always exact.
     """
 
-    def __init__(self, capacity: int, world_size: int, device, dtype, slots: int = 2, headroom: float = 0.02, group=None):
+    def __init__(self, capacity: int, world_size: int, device, dtype, slots: int = 2, headroom: float = 0.02, group=None, ctx=None):
         import torch
+        self.ctx = ctx
         self.world_size, self.capacity, self.slots, self.headroom, self.group = world_size, int(capacity), slots, headroom, group
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
@@ -231,6 +251,8 @@ class VisibleExchange:
         import torch
         import torch.distributed as dist
         assert self.pending[slot] is None, "slot still holds an uncollected frame"
+        if self.cuda:
+            check_same_stream(self.ctx)
         w1 = dist.all_gather_into_tensor(self.counts[slot], self.local_count[slot], group=self.group, async_op=True)
         if self.guess is None:
             w1.wait()
@@ -296,8 +318,9 @@ class RecordExchange:
     """
 
     def __init__(self, record_words: int, capacity: int, world_size: int, device, dtype, slots: int = 2, group=None,
-                 records_per_rank: int = 1):
+                 records_per_rank: int = 1, ctx=None):
         import torch
+        self.ctx = ctx
         self.world_size, self.record_words, self.capacity, self.slots, self.group = world_size, int(record_words), int(capacity), slots, group
         self.records_per_rank = int(records_per_rank)          # a rank that owns several scenes ships them together
         self.total_records = world_size * self.records_per_rank
@@ -315,6 +338,8 @@ class RecordExchange:
     def launch(self, slot: int) -> None:
         import torch.distributed as dist
         assert self.work[slot] is None, "slot still holds an unexpanded frame"
+        if self.gathered[slot].is_cuda:
+            check_same_stream(self.ctx)
         self.work[slot] = dist.all_gather_into_tensor(self.gathered[slot], self.local[slot], group=self.group, async_op=True)
 
     def ready(self, slot: int) -> bool:

@@ -106,6 +106,12 @@ class GpuContext:
     def SetStream(self, cuda_stream: int | None) -> None:
         check(self._lib.zn_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    def GetStream(self) -> int:
+        """The cudaStream_t (as an integer) all work of this context is enqueued on."""
+        p = C.c_void_p()
+        check(self._lib.zn_ctx_get_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
+
     def Sync(self) -> None:
         check(self._lib.zn_ctx_sync(self._h))
 
