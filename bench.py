@@ -308,7 +308,8 @@ class Rig:
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
                 os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
             dist.init_process_group("nccl", device_id=self.dev)
-        self.stream = torch.cuda.Stream(self.dev)
+        # high priority: the exchange's side stream (lowest priority) then yields SM slots to the frame's kernels
+        self.stream = torch.cuda.Stream(self.dev, priority=-1)
         torch.cuda.set_stream(self.stream)
         assert self.stream.cuda_stream != 0
         self.ctx = zn.GpuContext(self.local_rank, stream=self.stream.cuda_stream)
@@ -500,10 +501,11 @@ def make_exchange(rig: Rig, mode: str, words: int, E: int, records_per_rank: int
     IPC handles at set-up.  The torch-hosted variants are kept for comparison."""
     torch = rig.torch
     note = ""
-    if mode == "peer":
+    if mode in ("peer", "peer-overlap"):
         from zenyth_b200.peer_exchange import PeerExchange
         try:
-            return PeerExchange(rig.ctx, words, E, rig.world_size, rig.rank, records_per_rank=records_per_rank, slots=4), mode, note
+            return PeerExchange(rig.ctx, words, E, rig.world_size, rig.rank, records_per_rank=records_per_rank, slots=4,
+                                overlap=mode == "peer-overlap"), mode, note
         except RuntimeError as e:       # raised on every rank together: peer mapping is not possible on this box
             note, mode = f"--exchange peer unavailable ({e}); ran --exchange records", "records"
     if mode.startswith("peer"):
@@ -530,7 +532,9 @@ COLLECTIVE_NOTES = {
             "the level and emit kernels store the visibility record tile by tile into every peer's buffer (CUDA IPC mapped pointers); the kernel "
             "that follows the update on the stream raises a sequence flag at every peer (one fence.sys + relaxed sys-scope stores) and the "
             "expansion kernel's warps wait on the owners' flags themselves; every rank expands its peers' records into the ordered index "
-            "lists + counts (its own list comes straight from its emit kernel)",
+            "lists + counts one frame behind (its own list comes straight from its emit kernel); the timed region ends after the last expansion",
+    "peer-overlap": "as peer, but the expansion of frame k runs on a low-priority side stream right behind update(k) while the context stream "
+                    "already runs update(k+1); update(k) waits for the rank's own expansion of frame k-2 (ZN_EXCHANGE_OVERLAP)",
     "peer-nccl": "peer stores of the records + a 4-byte NCCL all-reduce per frame as the cross-rank barrier (torch-hosted variant)",
     "peer-waitkernel": "peer stores of the records; signal + wait as a launch of their own (torch-hosted variant)",
     "none": "none (1 GPU)",
@@ -579,6 +583,12 @@ def run_ours(args) -> None:
             exchange.launch(slot)                      # all-gather of frame k: overlaps what follows
             if exchange.ready(1 - slot):               # frame k-1 has arrived: derive every rank's list
                 exchange.expand(scene, 1 - slot, index_bases)
+        elif mode == "peer-overlap":
+            k = frame_no[0]
+            exchange.bind(scene, k)                    # (update(k) waits for this rank's own expand(k-2): flow control)
+            scene.Update()                             # kernels write this rank's record into every peer
+            exchange.expand(scene, k, index_bases)     # side stream: raises frame k's flags, waits on the device for the peers', derives
+                                                       # their lists while the next Update() already runs on the context stream
         elif use_peer:
             k = frame_no[0]
             exchange.bind(scene, k)
@@ -597,7 +607,9 @@ def run_ours(args) -> None:
             for slot in ((frame_no[0] - 2) % 2, (frame_no[0] - 1) % 2):
                 if exchange.ready(slot):
                     exchange.expand(scene, slot, index_bases)
-        if use_peer:
+        if mode == "peer-overlap":
+            exchange.join()                            # the context stream (and the timing event on it) waits for the last expansion
+        elif use_peer:
             for k in (frame_no[0] - 2, frame_no[0] - 1):
                 exchange.expand(scene, k, index_bases)
 
@@ -886,7 +898,12 @@ def scenes8_measure(rig: Rig, args, exchange_mode: str) -> dict:
 
     def step():
         k = frame_no[0]
-        if use_peer:
+        if mode == "peer-overlap":
+            exchange.bind(scenes, k)
+            for sc in scenes:
+                sc.Update()                              # kernels store the records into every peer as they run
+            exchange.expand(scenes[0], k, index_bases)   # side stream, overlaps the next step's updates
+        elif use_peer:
             exchange.bind(scenes, k)
             for sc in scenes:
                 sc.Update()                              # kernels store the records into every peer as they run
@@ -905,7 +922,9 @@ def scenes8_measure(rig: Rig, args, exchange_mode: str) -> dict:
         frame_no[0] += 1
 
     def finish():
-        if use_peer:
+        if mode == "peer-overlap":
+            exchange.join()
+        elif use_peer:
             for k in (frame_no[0] - 2, frame_no[0] - 1):
                 exchange.expand(scenes[0], k, index_bases)
         elif distributed:
@@ -974,7 +993,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["mesh64m", "scenes8x32m"], default="h8geo16m")
-    ap.add_argument("--exchange", choices=["peer", "records", "lists", "peer-nccl", "peer-waitkernel"], default="peer",
+    ap.add_argument("--exchange", choices=["peer", "peer-overlap", "records", "lists", "peer-nccl", "peer-waitkernel"], default="peer",
                     help="N>1: the kernels store the visibility records straight into peer GPUs' memory over NVLink and signal "
                          "completion with flags in peer memory (peer, default; falls back to records where peer mapping is refused); "
                          "NCCL all-gather of the records (records) or of the index lists (lists); peer stores with a 4-byte "

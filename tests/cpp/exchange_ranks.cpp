@@ -1,7 +1,7 @@
 // exchange_ranks.cpp — the multi-GPU host layer driven from C++ only: N processes (fork), a socket
 // hub as the host all-gather, Zenyth::PeerExchange over real CUDA IPC.  No torch, no NCCL, no Python.
 //
-//     exchange_ranks [world=2] [scenes_per_rank=1] [frames=9] [levels=7]
+//     exchange_ranks [world=2] [scenes_per_rank=1] [frames=9] [levels=7] [overlap=0]
 //
 // Rank r runs on GPU r % device_count, so with ONE GPU both ranks share cuda:0 (CUDA IPC between
 // processes on the same device is legal): IPC mapping, peer stores, flag stores and acquire loads
@@ -77,7 +77,7 @@ static CameraDesc camera_of_frame(int k) {
 	return c;
 }
 
-static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int levels, int fd) {
+static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int levels, bool overlap, int fd) {
 	try {
 		int devices = 0;
 		if (zn_device_count(&devices) != ZN_OK || devices < 1) { std::fprintf(stderr, "rank %u: no CUDA device\n", rank); return 3; }
@@ -120,6 +120,7 @@ static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int 
 		PeerExchangeDesc xd;
 		xd.worldSize = world; xd.rank = rank; xd.recordsPerRank = S; xd.allGather = all_gather; xd.user = &ch; xd.indexBases = bases;
 		xd.timeoutMs = 5000;
+		xd.overlap = overlap;
 		{
 			PeerExchange exchange(ctx, *scenes[0], xd);
 			std::vector<uint32_t> host;
@@ -141,18 +142,25 @@ static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int 
 				return true;
 			};
 			auto rendezvous = [&]() {
-				ctx.Sync();
 				uint32_t token = rank;
 				std::vector<uint32_t> all(world);
 				return all_gather(&ch, &token, all.data(), 4) == 0;
 			};
+			// default: Expand one frame behind, on the context stream; overlap: Expand the frame just updated, on the side stream
+			const int lag = overlap ? 0 : 1;
 			for (int k = 0; k < frames; ++k) {
 				const Camera cam(camera_of_frame(k));
 				exchange.Bind(ptrs, uint64_t(k));
 				for (Scene* s : ptrs) { s->SetCamera(cam); s->Update(); }
-				exchange.Expand(k - 1);     // raises this rank's frame-k flags; waits (on the device) for the peers' frame k-1 flags
-				if (lockstep && !rendezvous()) return 6;   // shared GPU: every flag the next launch waits for is up before it starts
-				if (k >= 1 && !verify(k - 1)) return 5;
+				if (lockstep) {
+					// shared GPU: raise the flags (no waiting), make sure every rank has, and only then launch a kernel that waits
+					exchange.Signal();
+					if (!rendezvous()) return 6;
+				}
+				exchange.Expand(k - lag);
+				if (k - lag >= 0 && (lockstep || k % 2 == 1)) {   // every frame in lockstep; every other one otherwise, so that frames really pipeline
+					if (!verify(k - lag)) return 5;
+				}
 			}
 			exchange.Expand(frames - 1);
 			if (!verify(frames - 1)) return 5;
@@ -173,6 +181,7 @@ int main(int argc, char** argv) {
 	const uint32_t S = argc > 2 ? uint32_t(std::atoi(argv[2])) : 1u;
 	const int frames = argc > 3 ? std::atoi(argv[3]) : 9;
 	const int levels = argc > 4 ? std::atoi(argv[4]) : 7;
+	const bool overlap = argc > 5 && std::atoi(argv[5]) != 0;
 	std::vector<int> hub_fds;
 	std::vector<pid_t> kids;
 	for (uint32_t r = 0; r < world; ++r) {
@@ -182,7 +191,7 @@ int main(int argc, char** argv) {
 		if (pid == 0) {
 			for (int fd : hub_fds) close(fd);
 			close(sv[0]);
-			std::exit(rank_main(r, world, S, frames, levels, sv[1]));
+			std::exit(rank_main(r, world, S, frames, levels, overlap, sv[1]));
 		}
 		close(sv[1]);
 		hub_fds.push_back(sv[0]);

@@ -143,7 +143,7 @@ TIMEOUT_MS = 5000 if shared else 2000
 sizes = [7 * 8 ** l for l in range(7)]
 E = sum(sizes)
 offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
-for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2), ("library", 1), ("library", 2)):
+for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2), ("library", 1), ("library", 2), ("library-overlap", 2)):
     if signal == "nccl" and shared:
         continue
     scenes, mine = [], []
@@ -155,8 +155,9 @@ for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2), ("library", 1), ("lib
         sc.Update()
         mine.append(sc.Visible().astype(np.int64))
         scenes.append(sc)
-    if signal == "library":     # the C++ host layer (zn_exchange_*): torch only carries the 64-byte handles at set-up
-        ex = PeerExchange(ctx, scenes[0].DeviceBuffers().visibility_record_words, E, world, rank, records_per_rank=S, timeout_ms=TIMEOUT_MS)
+    if signal.startswith("library"):     # the C++ host layer (zn_exchange_*): torch only carries the 64-byte handles at set-up
+        ex = PeerExchange(ctx, scenes[0].DeviceBuffers().visibility_record_words, E, world, rank, records_per_rank=S, timeout_ms=TIMEOUT_MS,
+                          overlap=signal == "library-overlap")
     else:
         ex = PeerRecordExchange(ctx, scenes[0].DeviceBuffers().visibility_record_words, E, world, rank, dev, torch.int32, signal=signal,
                                 records_per_rank=S, timeout_ms=TIMEOUT_MS)
@@ -165,11 +166,20 @@ for signal, S in (("flags", 1), ("nccl", 1), ("flags", 2), ("library", 1), ("lib
         ex.bind(scenes, k)
         for sc in scenes:
             sc.Update()
-        ex.launch(k)
-        ex.expand(scenes[0], k - 1, bases)
-        if shared:
-            torch.cuda.synchronize(dev)
-            dist.barrier()
+        if signal.startswith("library"):
+            if shared:                  # raise the flags (no waiting), make sure every rank has, only then launch the kernel that waits
+                ex.signal(scenes[0])
+                dist.barrier()
+            ex.expand(scenes[0], k if signal == "library-overlap" else k - 1, bases)
+            if shared and ex._lib is not None and (signal == "library-overlap" or k >= 1):
+                ex.result()
+                dist.barrier()
+        else:
+            ex.launch(k)
+            ex.expand(scenes[0], k - 1, bases)
+            if shared:
+                torch.cuda.synchronize(dev)
+                dist.barrier()
     ex.expand(scenes[0], 8, bases)
     counts, lists = ex.result()
     every = [None] * world
@@ -198,13 +208,13 @@ def test_two_processes_exchange_over_peer_memory(tmp_path):
     assert out.stdout.count("peer exchange ok") == 2
 
 
-@pytest.mark.parametrize("world,scenes_per_rank", [(2, 1), (2, 2), (3, 1)])
-def test_cpp_ranks_exchange_without_torch_or_nccl(world, scenes_per_rank):
+@pytest.mark.parametrize("world,scenes_per_rank,overlap", [(2, 1, 0), (2, 2, 0), (3, 1, 0), (2, 2, 1)])
+def test_cpp_ranks_exchange_without_torch_or_nccl(world, scenes_per_rank, overlap):
     """tests/cpp/exchange_ranks.cpp: fork()ed C++ processes, a socket hub as the host all-gather, Zenyth::PeerExchange,
     ShardScenes and SceneIndexBases of include/zenyth_b200.hpp — every gathered list of every frame is checked
     against the single-GPU result inside the program.  Ranks land on GPU rank % device_count."""
     from zenyth_b200 import build as zb
     exe = zb.build_cpp_tests()
-    out = subprocess.run([exe, str(world), str(scenes_per_rank), "9", "7"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, str(world), str(scenes_per_rank), "9", "7", str(overlap)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert out.stdout.count("exchange ok rank") == world

@@ -55,7 +55,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, vp, vp, vp, C.c_size_t)
 
 class ExchangeDesc(C.Structure):
     _fields_ = [("world_size", C.c_uint32), ("rank", C.c_uint32), ("records_per_rank", C.c_uint32), ("record_words", C.c_uint32),
-                ("list_capacity", C.c_uint32), ("slots", C.c_uint32), ("timeout_ms", C.c_uint32), ("allgather", ALLGATHER_FN), ("user", vp)]
+                ("list_capacity", C.c_uint32), ("slots", C.c_uint32), ("timeout_ms", C.c_uint32), ("allgather", ALLGATHER_FN), ("user", vp), ("flags", C.c_uint32)]
 
 
 # symbol -> (restype, argtypes).  tests/test_abi.py checks this table against include/zenyth_b200.h.
@@ -133,6 +133,8 @@ PROTOTYPES = {
     "zn_exchange_unbind": (C.c_int, [vp, vp, C.c_uint32]),
     "zn_exchange_bind": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64]),
     "zn_exchange_expand": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "zn_exchange_signal": (C.c_int, [vp, vp]),
+    "zn_exchange_join": (C.c_int, [vp]),
     "zn_exchange_result": (C.c_int, [vp, vp, C.POINTER(vp), c_u32_p]),
     "zn_exchange_info": (C.c_int, [vp, c_u32_p, c_u32_p, C.POINTER(C.c_uint64)]),
     "zn_mesh_create": (C.c_int, [vp, C.POINTER(MeshDesc), C.POINTER(vp)]),

@@ -94,10 +94,15 @@ int zn_ctx_create(int device_ordinal, zn_ctx** out_ctx) {
 	zn_ctx* c = new zn_ctx();
 	c->device = device_ordinal;
 	c->sm_count = prop.multiProcessorCount;
-	const cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+	// The context's own stream gets the highest priority the device offers: side work that overlaps a frame
+	// (the exchange's expansion kernels, zn_exchange_*) runs at the lowest, so that the block scheduler
+	// hands freed SM slots to the frame's latency-bound small levels first.
+	int least = 0, greatest = 0;
+	cudaDeviceGetStreamPriorityRange(&least, &greatest);
+	const cudaError_t e = cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, greatest);
 	if (e != cudaSuccess) {
 		delete c;
-		return zn::fail(ZN_ERR_CUDA, "zn_ctx_create: cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(e));
+		return zn::fail(ZN_ERR_CUDA, "zn_ctx_create: cudaStreamCreateWithPriority failed: %s", cudaGetErrorString(e));
 	}
 	c->stream = c->own_stream;
 	*out_ctx = c;

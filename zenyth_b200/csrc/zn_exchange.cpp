@@ -20,13 +20,29 @@
 // all-gather for the 64-byte handles at set-up — MPI_Allgather, a socket, torch.distributed: any
 // channel — and it is never called per frame.
 //
-// Pipeline per frame k:   zn_exchange_bind(k); zn_scene_update of every owned scene; zn_exchange_expand(k-1).
-// Slot reuse.  Update(k+1) on rank r stores into slot (k+1) % slots of every peer p.  It is
+// Pipeline per frame k (default, everything on the context stream, the expansion one frame behind):
+//     zn_exchange_bind(k); zn_scene_update of every owned scene; zn_exchange_expand(k-1).
+// The expansion launch raises this rank's flags for frame k (the update before it on the stream is
+// complete) and waits on the device for the peers' frame k-1 flags — which, one frame later, are
+// normally up already: the frame of slack absorbs jitter between ranks and no CTA spins.
+// Slot reuse.  Update(k+1) on rank r stores into slot (k+1) % 4 of every peer p.  It is
 // stream-ordered after r's expand(k-1), which waited for p's frame k-1 signal; p raised it in the
-// launch after its update(k-1), i.e. after its expand(k-3) was enqueued... so the youngest frame a
+// launch after its update(k-1), i.e. after its expand(k-3) was enqueued — so the youngest frame a
 // peer is guaranteed to have finished reading is k-3 and a slot may be reused after FOUR frames.
 // Lists are double-buffered: lists[k % 2] is complete (all ranks' lists) once expand(k) has run and
-// is overwritten by update(k+2).
+// its own-rank part is overwritten by update(k+2).
+//
+// ZN_EXCHANGE_OVERLAP (opt-in): the expansion of frame k runs on the exchange's own low-priority SIDE
+// STREAM right behind update(k) (ordered by an event) while the context stream already runs
+// update(k+1); update(f) then waits for the rank's OWN expand(f-2) (cudaStreamWaitEvent), which bounds
+// the drift between ranks to two frames and keeps the four slots safe by the same argument (p's
+// update(f) follows p's expand(f-2), which saw my flag f-1, raised by my expand(f-2) launch — behind my
+// expand(f-4) on my side stream).  Measured: it buys ~1% (N = 8: 0.594 vs 0.600 ms per frame; one GPU
+// emulation, update + expansion of 7 records: 573 vs 577 us, scripts/overlap_probe.py) — the frame
+// already runs at 0.99 of the HBM roofline, so there is no idle bandwidth for the expansion's writes to
+// hide in: N lists on every rank cost their bytes (roofline.scaling_ceiling in bench.py).  It is kept
+// as an option because a frame with less traffic per entity (zn_scene_cull passes, small scenes) does
+// leave room.
 #include "zn_internal.hpp"
 
 #include <algorithm>
@@ -53,6 +69,10 @@ struct zn_exchange {
 	uint32_t* status = nullptr;              // [1]
 	uint32_t* host_counts = nullptr;         // pinned [total + 1]
 	int64_t issued = -1, expanded = -1;
+	cudaStream_t side = nullptr;             // the expansions run here, concurrently with the next update on the context stream
+	cudaEvent_t updated = nullptr;           // context stream: everything up to and including update(frame) is enqueued
+	cudaEvent_t done[2] = {nullptr, nullptr};// side stream: expand(frame) complete, by frame parity
+	bool overlap = false;
 };
 
 using namespace zn;
@@ -70,6 +90,11 @@ static void exchange_release(zn_exchange* x) {
 	if (x->status) cudaFree(x->status);
 	if (x->host_counts) cudaFreeHost(x->host_counts);
 	x->lists = x->counts = x->status = x->host_counts = nullptr;
+	if (x->updated) cudaEventDestroy(x->updated);
+	for (cudaEvent_t& e : x->done) { if (e) cudaEventDestroy(e); e = nullptr; }
+	if (x->side) cudaStreamDestroy(x->side);
+	x->updated = nullptr;
+	x->side = nullptr;
 }
 
 extern "C" {
@@ -167,6 +192,7 @@ int zn_exchange_create(zn_ctx* ctx, const zn_exchange_desc* d, zn_exchange** out
 	x->record_words = d->record_words; x->capacity = d->list_capacity;
 	x->slots = d->slots ? d->slots : 4; x->timeout_ms = d->timeout_ms ? d->timeout_ms : 2000;
 	x->allgather = d->allgather; x->user = d->user;
+	x->overlap = (d->flags & ZN_EXCHANGE_OVERLAP) != 0;
 	x->slot_bytes = size_t(x->total) * x->record_words * 4;
 	x->flags_offset = (x->slots * x->slot_bytes + 127) / 128 * 128;
 	// Set-up is collective: a rank that cannot allocate, export or map still takes part in every
@@ -211,8 +237,18 @@ int zn_exchange_create(zn_ctx* ctx, const zn_exchange_desc* d, zn_exchange** out
 		const size_t list_words = size_t(2) * x->total * x->capacity;
 		if (cudaMalloc(&x->lists, list_words * 4) != cudaSuccess || cudaMalloc(&x->counts, size_t(2) * x->total * 4) != cudaSuccess ||
 		    cudaMalloc(&x->status, 4) != cudaSuccess || cudaHostAlloc(&x->host_counts, (size_t(x->total) + 1) * 4, cudaHostAllocDefault) != cudaSuccess ||
-		    cudaMemset(x->counts, 0, size_t(2) * x->total * 4) != cudaSuccess || cudaMemset(x->status, 0, 4) != cudaSuccess)
+		    cudaMemset(x->counts, 0, size_t(2) * x->total * 4) != cudaSuccess || cudaMemset(x->status, 0, 4) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&x->updated, cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&x->done[0], cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&x->done[1], cudaEventDisableTiming) != cudaSuccess)
 			snprintf(problem, sizeof(problem), "rank %u: cannot allocate the list buffers: %s", x->rank, cudaGetErrorString(cudaGetLastError()));
+	}
+	if (everyone && !problem[0]) {
+		// the side stream runs at the LOWEST priority: the frame on the context stream goes first wherever both want an SM slot
+		int least = 0, greatest = 0;
+		cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		if (cudaStreamCreateWithPriority(&x->side, cudaStreamNonBlocking, least) != cudaSuccess)
+			snprintf(problem, sizeof(problem), "rank %u: cannot create the side stream: %s", x->rank, cudaGetErrorString(cudaGetLastError()));
 	}
 	// second rendezvous: every rank has mapped every buffer before anyone writes — and every rank hears of any failure
 	Hello second = {};
@@ -249,6 +285,7 @@ int zn_exchange_destroy(zn_exchange* x, zn_scene* const* scenes, uint32_t scene_
 	zn_exchange_unbind(x, scenes, scene_count);
 	cudaSetDevice(x->ctx->device);
 	cudaStreamSynchronize(x->ctx->stream);
+	if (x->side) cudaStreamSynchronize(x->side);
 	// nobody may still be writing into a buffer that is about to go away: rendezvous, release, rendezvous
 	uint32_t token = x->rank;
 	std::vector<uint32_t> tokens(x->world);
@@ -265,6 +302,9 @@ int zn_exchange_bind(zn_exchange* x, zn_scene* const* scenes, uint32_t scene_cou
 	ZN_REQUIRE(scene_count == x->per_rank, "zn_exchange_bind: %u scenes given, this rank owns %u records", scene_count, x->per_rank);
 	ZN_REQUIRE(int64_t(frame) == x->issued + 1, "zn_exchange_bind: frames are bound in order (expected %lld)", (long long)(x->issued + 1));
 	const uint32_t slot = uint32_t(frame % x->slots);
+	ZN_CUDA(cudaSetDevice(x->ctx->device));
+	// flow control: update(frame) may not start before this rank's own expand(frame-2) has completed
+	if (x->overlap && x->expanded >= int64_t(frame) - 2 && frame >= 2) ZN_CUDA(cudaStreamWaitEvent(x->ctx->stream, x->done[frame % 2], 0));
 	for (uint32_t j = 0; j < scene_count; ++j) {
 		zn_scene* sc = scenes[j];
 		ZN_REQUIRE(sc && sc->ctx == x->ctx, "zn_exchange_bind: scene %u is NULL or belongs to another context", j);
@@ -293,24 +333,50 @@ int zn_exchange_bind(zn_exchange* x, zn_scene* const* scenes, uint32_t scene_cou
 	return ZN_OK;
 }
 
-int zn_exchange_expand(zn_exchange* x, zn_scene* scene, int64_t frame, const uint32_t* index_bases) {
-	ZN_REQUIRE(x && scene, "zn_exchange_expand: NULL argument");
-	if (frame < 0 && x->issued == 0 && x->expanded < 0) {
-		// Frame 0 has been updated and there is nothing to expand yet: a signal-only launch (every record
-		// skipped) raises its flags now instead of one frame later, so no peer ever waits on this rank's
-		// first flag longer than it must.
-		return zn_scene_expand_visible_signalled(scene, x->base, x->total, x->record_words, 0, x->total, nullptr, x->lists, x->capacity, x->counts,
-		                                         x->base + x->flags_offset, kFlagStrideWords, x->per_rank, 0u, x->timeout_ms, x->status);
+static int exchange_launch(zn_exchange* x, zn_scene* scene, int64_t frame, const uint32_t* index_bases, bool signal_only) {
+	ZN_CUDA(cudaSetDevice(x->ctx->device));
+	cudaStream_t stream = x->ctx->stream;
+	if (x->overlap) {
+		// side stream, behind everything enqueued on the context stream so far (the update of `frame` included)
+		ZN_CUDA(cudaEventRecord(x->updated, x->ctx->stream));
+		ZN_CUDA(cudaStreamWaitEvent(x->side, x->updated, 0));
+		stream = x->side;
 	}
-	if (frame < 0 || frame > x->issued || frame <= x->expanded) return ZN_OK;   // never issued, or already expanded
-	ZN_REQUIRE(frame == x->expanded + 1, "zn_exchange_expand: frames are expanded in order (expected %lld)", (long long)(x->expanded + 1));
 	const uint8_t* records = x->base + size_t(frame % x->slots) * x->slot_bytes;
 	const size_t half = size_t(frame % 2) * x->total;
-	const int rc = zn_scene_expand_visible_signalled(scene, records, x->total, x->record_words, int(x->rank * x->per_rank), x->per_rank, index_bases,
-	                                                 x->lists + half * x->capacity, x->capacity, x->counts + half, x->base + x->flags_offset,
-	                                                 kFlagStrideWords, x->per_rank, uint32_t(frame + 1), x->timeout_ms, x->status);
+	const uint32_t first_own = x->rank * x->per_rank;
+	return expand_visible_on(stream, scene, signal_only ? "zn_exchange_signal" : "zn_exchange_expand", records, x->total, x->record_words,
+	                         signal_only ? 0 : int(first_own), signal_only ? x->total : x->per_rank, index_bases, x->lists + half * x->capacity,
+	                         x->capacity, x->counts + half, x->base + x->flags_offset, kFlagStrideWords, x->per_rank, uint32_t(frame + 1),
+	                         x->timeout_ms, x->status, nullptr);
+}
+
+int zn_exchange_signal(zn_exchange* x, zn_scene* scene) {
+	ZN_REQUIRE(x && scene, "zn_exchange_signal: NULL argument");
+	if (x->issued < 0) return fail(ZN_ERR_STATE, "zn_exchange_signal: no frame has been bound yet");
+	const int rc = exchange_launch(x, scene, x->issued, nullptr, true);
 	if (rc != ZN_OK) return rc;
+	// synchronous: when this returns the flags are up (the update they announce is complete)
+	ZN_CUDA(cudaStreamSynchronize(x->overlap ? x->side : x->ctx->stream));
+	return ZN_OK;
+}
+
+int zn_exchange_expand(zn_exchange* x, zn_scene* scene, int64_t frame, const uint32_t* index_bases) {
+	ZN_REQUIRE(x && scene, "zn_exchange_expand: NULL argument");
+	if (frame < 0 || frame > x->issued || frame <= x->expanded) return ZN_OK;   // never issued, or already expanded
+	ZN_REQUIRE(frame == x->expanded + 1, "zn_exchange_expand: frames are expanded in order (expected %lld)", (long long)(x->expanded + 1));
+	const int rc = exchange_launch(x, scene, frame, index_bases, false);
+	if (rc != ZN_OK) return rc;
+	if (x->overlap) ZN_CUDA(cudaEventRecord(x->done[frame % 2], x->side));
 	x->expanded = frame;
+	return ZN_OK;
+}
+
+int zn_exchange_join(zn_exchange* x) {
+	ZN_REQUIRE(x, "zn_exchange_join: exchange is NULL");
+	if (!x->overlap || x->expanded < 0) return ZN_OK;
+	ZN_CUDA(cudaSetDevice(x->ctx->device));
+	ZN_CUDA(cudaStreamWaitEvent(x->ctx->stream, x->done[x->expanded % 2], 0));
 	return ZN_OK;
 }
 
@@ -318,6 +384,7 @@ int zn_exchange_result(zn_exchange* x, uint32_t* out_counts, void** out_lists_de
 	ZN_REQUIRE(x, "zn_exchange_result: exchange is NULL");
 	if (x->expanded < 0) return fail(ZN_ERR_STATE, "zn_exchange_result: no frame has been expanded yet");
 	ZN_CUDA(cudaSetDevice(x->ctx->device));
+	if (x->overlap) ZN_CUDA(cudaStreamWaitEvent(x->ctx->stream, x->done[x->expanded % 2], 0));
 	const size_t half = size_t(x->expanded % 2) * x->total;
 	ZN_CUDA(cudaMemcpyAsync(x->host_counts, x->counts + half, size_t(x->total) * 4, cudaMemcpyDeviceToHost, x->ctx->stream));
 	ZN_CUDA(cudaMemcpyAsync(x->host_counts + x->total, x->status, 4, cudaMemcpyDeviceToHost, x->ctx->stream));

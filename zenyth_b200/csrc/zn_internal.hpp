@@ -40,6 +40,14 @@ int encode_matrix_tensor_map(CUtensorMap* out, void* base, uint64_t rows);
 
 } // namespace zn
 
+struct zn_scene;
+namespace zn {
+int expand_visible_on(cudaStream_t stream, zn_scene* s, const char* who, const void* records_dev, uint32_t record_count,
+                      uint32_t record_stride_words, int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev,
+                      uint32_t list_stride, void* counts_dev, const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag,
+                      uint32_t expected, uint32_t timeout_ms, void* status_dev, const void* abort_status);
+} // namespace zn
+
 struct zn_ctx {
 	int device = 0;
 	int sm_count = 0;

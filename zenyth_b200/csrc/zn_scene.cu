@@ -319,10 +319,14 @@ int zn_scene_set_signal_value(zn_scene* s, uint32_t value) {
 	return ZN_OK;
 }
 
-static int expand_visible(zn_scene* s, const char* who, const void* records_dev, uint32_t record_count, uint32_t record_stride_words,
-                          int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
-                          const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
-                          uint32_t timeout_ms, void* status_dev, const void* abort_status) {
+} // extern "C"
+
+// The expansion launch on a stream of the caller's choice (the C-ABI entry points use the context
+// stream; zn_exchange_* runs it on its side stream so that it overlaps the next frame's update).
+int zn::expand_visible_on(cudaStream_t stream, zn_scene* s, const char* who, const void* records_dev, uint32_t record_count,
+                          uint32_t record_stride_words, int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev,
+                          uint32_t list_stride, void* counts_dev, const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag,
+                          uint32_t expected, uint32_t timeout_ms, void* status_dev, const void* abort_status) {
 	ZN_REQUIRE(s && records_dev && lists_dev && counts_dev, "%s: NULL argument", who);
 	ZN_REQUIRE(record_count >= 1 && record_count <= 64, "%s: record_count %u must be in [1, 64]", who, record_count);
 	ZN_REQUIRE(record_stride_words >= s->record_words, "%s: record stride %u < record size %u words", who, record_stride_words, s->record_words);
@@ -340,7 +344,7 @@ static int expand_visible(zn_scene* s, const char* who, const void* records_dev,
 	// One CTA per (record, chunk), one warp per 4-tile group.
 	if (record_count == skip_count && !flags_dev) return ZN_OK;     // nothing to expand and nothing to signal
 	const dim3 grid((s->chunk_count + kExpandChunks - 1) / kExpandChunks, std::max<uint32_t>(1u, record_count - skip_count));
-	expand_visible_kernel<<<grid, kExpandWarps * 32, 0, s->ctx->stream>>>(
+	expand_visible_kernel<<<grid, kExpandWarps * 32, 0, stream>>>(
 		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count,
 		skip_index, int(skip_count), static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),
 		static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag, uint64_t(timeout_ms) * 1000000ull,
@@ -349,12 +353,14 @@ static int expand_visible(zn_scene* s, const char* who, const void* records_dev,
 	return ZN_OK;
 }
 
+extern "C" {
+
 int zn_scene_expand_visible(zn_scene* s, const void* records_dev, uint32_t record_count, uint32_t record_stride_words, int skip_index,
                             const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev) {
 	ZN_REQUIRE(s, "zn_scene_expand_visible: scene is NULL");
 	const void* abort_status = s->abort_status;   // set by a zn_scene_wait_flags on this scene: a timed-out wait cancels this expansion
 	s->abort_status = nullptr;
-	return expand_visible(s, "zn_scene_expand_visible", records_dev, record_count, record_stride_words, skip_index, 1, index_bases, lists_dev,
+	return expand_visible_on(s->ctx->stream, s, "zn_scene_expand_visible", records_dev, record_count, record_stride_words, skip_index, 1, index_bases, lists_dev,
 	                      list_stride, counts_dev, nullptr, 0, 1, 0, 0, nullptr, abort_status);
 }
 
@@ -365,7 +371,7 @@ int zn_scene_expand_visible_signalled(zn_scene* s, const void* records_dev, uint
 	ZN_REQUIRE(flags_dev && status_dev, "zn_scene_expand_visible_signalled: flags_dev / status_dev is NULL");
 	ZN_REQUIRE(records_per_flag >= 1 && timeout_ms >= 1, "zn_scene_expand_visible_signalled: records_per_flag and timeout_ms must be >= 1");
 	ZN_REQUIRE(skip_count <= record_count, "zn_scene_expand_visible_signalled: skip_count %u > record_count %u", skip_count, record_count);
-	return expand_visible(s, "zn_scene_expand_visible_signalled", records_dev, record_count, record_stride_words, skip_index, skip_count, index_bases,
+	return expand_visible_on(s->ctx->stream, s, "zn_scene_expand_visible_signalled", records_dev, record_count, record_stride_words, skip_index, skip_count, index_bases,
 	                      lists_dev, list_stride, counts_dev, flags_dev, flag_stride_words, records_per_flag, expected, timeout_ms, status_dev, nullptr);
 }
 

@@ -52,7 +52,7 @@ class PeerExchange:
     """zn_exchange_* behind the engine-idiom names (mirrors Zenyth::PeerExchange in zenyth_b200.hpp)."""
 
     def __init__(self, ctx, record_words: int, capacity: int, world_size: int, rank: int, records_per_rank: int = 1,
-                 slots: int = 4, timeout_ms: int = 2000, allgather=None, group=None):
+                 slots: int = 4, timeout_ms: int = 2000, allgather=None, group=None, overlap: bool = False):
         import ctypes as C
 
         from . import _capi
@@ -78,7 +78,7 @@ class PeerExchange:
 
         self._cb = _capi.ALLGATHER_FN(trampoline if world_size > 1 else (lambda *a: 0))   # kept alive with the object
         desc = _capi.ExchangeDesc(self.world_size, self.rank, self.records_per_rank, int(record_words), self.capacity, int(slots),
-                                  self.timeout_ms, self._cb, None)
+                                  self.timeout_ms, self._cb, None, 1 if overlap else 0)
         h = C.c_void_p()
         rc = self._lib.zn_exchange_create(ctx._h, C.byref(desc), C.byref(h))
         if rc != 0:
@@ -106,7 +106,19 @@ class PeerExchange:
     def launch(self, frame: int) -> None:      # interface parity with the torch-hosted variants: nothing to launch
         return None
 
+    def signal(self, scene) -> None:
+        """Raise this rank's flags for the last bound frame without waiting for anyone; returns when they are up.
+        Only ranks that SHARE one GPU need it (signal, host barrier, then expand)."""
+        self._capi.check(self._lib.zn_exchange_signal(self._h, scene._h))
+
+    def join(self) -> None:
+        """Make the context stream wait for the last expansion (overlap=True: it runs on the side stream; else a no-op)."""
+        self._capi.check(self._lib.zn_exchange_join(self._h))
+
     def expand(self, scene, frame: int, index_bases=None) -> None:
+        """Asynchronous: raise this rank's flags for the last bound frame, wait on the device for the owners' flags of
+        `frame`, derive their lists.  Default pattern: expand(k - 1) after Update(k); with overlap=True (side stream):
+        expand(k) right after Update(k)."""
         import numpy as np
         bases = None if index_bases is None else np.ascontiguousarray(index_bases, np.uint32)
         self._keep = bases
