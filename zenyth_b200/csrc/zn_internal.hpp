@@ -72,6 +72,7 @@ struct zn_scene {
 	uint32_t tile_count = 0;
 	uint32_t index_base = 0;
 	int max_ctas = 0;              // co-resident CTAs of the persistent level kernel (4 per SM)
+	int max_ctas_world = 0;        // ... of its world-only form (5 per SM: no MVP tile in shared memory)
 	bool has_camera = false;
 	bool world_valid = false;      // an update has run: the world matrices exist (zn_scene_cull needs them)
 	bool last_update_had_view = false;

@@ -25,8 +25,8 @@ static cudaError_t set_kernel_attributes() {
 	if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
 	ZN_ATTR((scene_level_kernel<true, true>), kLevelSmem)
 	ZN_ATTR((scene_level_kernel<false, true>), kLevelSmem)
-	ZN_ATTR((scene_level_kernel<true, false>), kLevelSmem)
-	ZN_ATTR((scene_level_kernel<false, false>), kLevelSmem)
+	ZN_ATTR((scene_level_kernel<true, false>), kWorldSmem)
+	ZN_ATTR((scene_level_kernel<false, false>), kWorldSmem)
 	ZN_ATTR(scene_cull_kernel, kCullSmem)
 #undef ZN_ATTR
 	return cudaSuccess;
@@ -122,6 +122,12 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, scene_level_kernel<false, true>, kTile, kLevelSmem));
 	ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, scene_cull_kernel, kTile, kCullSmem));
 	s->max_ctas = std::min(per_sm_a, per_sm_b) * ctx->sm_count;
+	{
+		int wa = 0, wb = 0;
+		ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wa, scene_level_kernel<true, false>, kTile, kWorldSmem));
+		ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wb, scene_level_kernel<false, false>, kTile, kWorldSmem));
+		s->max_ctas_world = std::max(1, std::min(wa, wb)) * ctx->sm_count;
+	}
 	s->max_ctas_cull = per_sm_c * ctx->sm_count;
 	if (s->max_ctas < 1 || s->max_ctas_cull < 1) { delete s; return fail(ZN_ERR_CUDA, "zn_scene_create: a scene kernel does not fit on an SM"); }
 	uint32_t tile_base = 0;
@@ -468,12 +474,12 @@ static int run_update(zn_scene* s, bool with_view) {
 	pdl.val.programmaticStreamSerializationAllowed = 1;
 	cudaLaunchConfig_t cfg = {};
 	cfg.blockDim = dim3(kTile);
-	cfg.dynamicSmemBytes = kLevelSmem;
+	cfg.dynamicSmemBytes = with_view ? kLevelSmem : kWorldSmem;
 	cfg.stream = ctx->stream;
 	cfg.attrs = &pdl;
 	for (size_t l = 0; l < s->levels.size(); ++l) {
 		zn_level& lv = s->levels[l];
-		const uint32_t grid = std::min<uint32_t>(lv.tiles, uint32_t(s->max_ctas));
+		const uint32_t grid = std::min<uint32_t>(lv.tiles, uint32_t(with_view ? s->max_ctas : s->max_ctas_world));
 		cfg.gridDim = dim3(grid);
 		cfg.numAttrs = ((l == 0 && s->inputs_touched) || prof) ? 0 : 1;
 		if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[l], ctx->stream));

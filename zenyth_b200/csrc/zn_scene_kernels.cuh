@@ -47,6 +47,7 @@ constexpr uint32_t kParSlots = 64;                         // parent matrices st
 constexpr uint32_t kParBytes = kParSlots * 64;             // 4 KiB
 constexpr uint32_t kOutBytes = 2 * kTile * 64;             // world tile + mvp tile
 constexpr uint32_t kLevelSmem = kOutBytes + kInBytes + kParBytes + 1024;
+constexpr uint32_t kWorldSmem = kTile * 64 + kInBytes + kParBytes + 1024;   // WITH_VIEW = false: no MVP tile, 37 KiB, five CTAs per SM
 constexpr uint32_t kGather = 0xFFFFFFFFu;                  // tile_prange.y: parents too scattered to stage
 constexpr int kChunkTiles = 32;                            // tiles per emit CTA (8192 entities)
 constexpr uint32_t kSmallLevelTiles = 4096;                // levels below 1Mi entities leave their peer stores to the emit kernel
@@ -96,7 +97,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // rows 0..8 and the parent row of a block (10 KiB instead of 16), stores the world tile and writes
 // neither MVPs nor masks; a later scene_cull_kernel pass supplies those per camera.
 template <bool HAS_PARENT, bool WITH_VIEW>
-__global__ void __launch_bounds__(kTile, 4)
+__global__ void __launch_bounds__(kTile, WITH_VIEW ? 4 : 5)
 scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_constant__ CUtensorMap tm_mvp,
                    const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
                    const uint2* __restrict__ tile_prange, const float* __restrict__ world_rd,
@@ -111,10 +112,11 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 
 	// 1024-byte aligned tiles (the swizzle pattern is a function of the shared address bits)
 	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	constexpr uint32_t out_bytes = WITH_VIEW ? kOutBytes : uint32_t(kTile) * 64u;
 	float4* out_world = reinterpret_cast<float4*>(smem);
-	float4* out_mvp = reinterpret_cast<float4*>(smem + kTile * 64);
-	const uint32_t* in_blk = reinterpret_cast<const uint32_t*>(smem + kOutBytes);
-	const float4* in_par = reinterpret_cast<const float4*>(smem + kOutBytes + kInBytes);
+	float4* out_mvp = reinterpret_cast<float4*>(smem + kTile * 64);   // WITH_VIEW only
+	const uint32_t* in_blk = reinterpret_cast<const uint32_t*>(smem + out_bytes);
+	const float4* in_par = reinterpret_cast<const float4*>(smem + out_bytes + kInBytes);
 
 	const int t = threadIdx.x;
 	const int lane = t & 31;
