@@ -8,6 +8,11 @@
 // (Core/include/IRenderer.hpp:5-12) and is installed with Application::SetRenderer exactly as
 // Sandbox/src/main.cpp:21-22 installs D3D12Renderer.  The scene is the config-1 stand-in of
 // a 5-level tree, fan-out 8, 4,681 entities, 1280x720 viewport.
+//
+// The path is called where SURVEY.md §8(b) says it would be: Scene::UpdateWorld() from OnUpdate(dt)
+// (Core/src/Application.cpp:47) and Scene::Cull(camera) from OnRender(), between the renderer's
+// BeginFrame and EndFrame (Application.cpp:49-51).  At shutdown the last frame is repeated through
+// the fused Scene::Update() with the same camera and must give the same visible list.
 #include "pch.hpp"
 #include "Application.hpp"
 
@@ -37,10 +42,7 @@ class GpuSceneRenderer : public Zenyth::IRenderer {
 public:
 	explicit GpuSceneRenderer(SharedState& st) : m_st(st) {}
 	void Init(HWND, uint32_t width, uint32_t height) override { m_st.camera.Resize(width, height); }
-	void BeginFrame() override {
-		m_st.scene->SetCamera(m_st.camera);
-		m_st.scene->Update();
-	}
+	void BeginFrame() override {}            // nothing to prepare: the world matrices were composed in OnUpdate
 	void EndFrame() override {
 		m_st.visible = m_st.scene->VisibleCount();
 		++m_st.frames;
@@ -95,12 +97,23 @@ protected:
 	void OnUpdate(float dt) override {
 		m_root.rotation.y += dt;                // yaw += dt
 		m_st.scene->SetTransform(0, m_root);
+		m_st.scene->UpdateWorld();              // Scene::Update(dt): TRS -> world over the hierarchy
 	}
-	void OnRender() override {}
-	void OnShutdown() override { m_totalTime = GetTimer().TotalTime(); }
+	void OnRender() override {
+		m_st.scene->Cull(m_st.camera);          // Scene::Cull(camera): MVP + frustum test + ordered visible list
+	}
+	void OnShutdown() override {
+		m_totalTime = GetTimer().TotalTime();
+		// the same frame through the fused call: identical list
+		const std::vector<uint32_t> split = m_st.scene->Visible();
+		m_st.scene->SetCamera(m_st.camera);
+		m_st.scene->Update();
+		m_splitEqualsFused = split == m_st.scene->Visible();
+	}
 
 public:
 	double m_totalTime = 0.0;
+	bool m_splitEqualsFused = false;
 
 private:
 	SharedState& m_st;
@@ -115,8 +128,10 @@ int main() {
 		SandboxApp app(st);
 		app.SetRenderer(std::make_unique<GpuSceneRenderer>(st));   // Sandbox/src/main.cpp:21-22
 		app.Run();                                                  // Core/src/Application.cpp:26-57
-		std::printf("{\"entities\": 4681, \"frames\": %u, \"resizes\": %u, \"visible\": %u, \"ms_per_frame\": %.4f, \"aspect\": %.4f}\n",
-		            st.frames, st.resizes, st.visible, st.frames ? app.m_totalTime * 1e3 / st.frames : 0.0, st.camera.Desc().aspect);
+		std::printf("{\"entities\": 4681, \"frames\": %u, \"resizes\": %u, \"visible\": %u, \"ms_per_frame\": %.4f, \"aspect\": %.4f, "
+		            "\"split_equals_fused\": %s}\n",
+		            st.frames, st.resizes, st.visible, st.frames ? app.m_totalTime * 1e3 / st.frames : 0.0, st.camera.Desc().aspect,
+		            app.m_splitEqualsFused ? "true" : "false");
 	} catch (const std::runtime_error& e) {
 		std::fprintf(stderr, "sandbox_reference_loop: %s\n", e.what());
 		return 2;

@@ -53,6 +53,19 @@ def expand():
 
 out = {"update_only_us": timed(sc.Update)}
 out["expand_only_us"] = timed(expand)
+# the signalled form with every flag already up: what the acquire (LDG.STRONG.SYS + CCTL.IVALL per CTA) costs
+flags = torch.full((R * 32,), 1 << 20, dtype=torch.int32, device=dev)
+status = torch.zeros(1, dtype=torch.int32, device=dev)
+torch.cuda.synchronize()
+
+
+def expand_signalled():
+    sc.ExpandVisibleSignalled(recs.data_ptr() + 4 * words, R, words, lists.data_ptr(), E, counts.data_ptr(), flags.data_ptr(), 32, 1,
+                              status.data_ptr(), skip_index=-1, skip_count=0)
+
+
+out["expand_signalled_flags_up_us"] = timed(expand_signalled)
+assert status.item() == 0
 
 
 def serial():

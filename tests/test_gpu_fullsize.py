@@ -219,3 +219,4 @@ def test_reference_application_loop_drives_the_gpu_scene(gpu_ctx):
     assert out["entities"] == 4681 and out["frames"] == 150 and out["resizes"] == 1
     assert 0 < out["visible"] <= 4681
     assert abs(out["aspect"] - 2.0) < 1e-3                # Application::OnEvent forwarded the 1600x800 resize to IRenderer::Resize
+    assert out["split_equals_fused"] is True              # OnUpdate -> UpdateWorld, OnRender -> Cull: the same list as the fused Update

@@ -238,13 +238,18 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 			if (lane < kWarpsPerTile) rec.ptr[0][header_words + size_t(gt) * kWarpsPerTile + lane] = word;
 			const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(word));
 			if (lane == 0) atomicAdd(chunk_total + gt / kChunkTiles, cnt);
-		} else if (warp == kWarpsPerTile - 1 && rec.n > 1 && lane < kWarpsPerTile) {
+		} else if (warp == kWarpsPerTile - 1 && rec.n > 1) {
 			// ... and, over NVLink, straight into the copy of this rank's record that every peer keeps
 			// (fused all-gather: plain stores to mapped peer memory).  Issued by the last warp so the
-			// TMA-issuing warp never queues behind remote stores.
-			const uint32_t word = s_mask[lane];
-			const size_t at = header_words + size_t(tile_base + tl) * kWarpsPerTile + lane;
-			for (int q = 1; q < rec.n; ++q) rec.ptr[q][at] = word;
+			// TMA-issuing warp never queues behind remote stores, and spread over its lanes — lane l
+			// carries word l % 8 to peer 1 + l / 8 (+ 4 in a second round) — so seven peers cost two
+			// store instructions per tile instead of seven on the CTA's critical path (7 us per frame
+			// at N = 8, measured with local targets).
+			const uint32_t word = s_mask[lane & 7];
+			const size_t at = header_words + size_t(tile_base + tl) * kWarpsPerTile + (lane & 7);
+			const int q0 = 1 + (lane >> 3);
+			if (q0 < rec.n) rec.ptr[q0][at] = word;
+			if (q0 + 4 < rec.n) rec.ptr[q0 + 4][at] = word;
 		}
 	}
 	if (t == 0) bulk_wait_read_all();
@@ -354,11 +359,13 @@ scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_con
 			bulk_commit();
 		}
 		if (warp == 0) {
-			const uint32_t word = (lane < kWarpsPerTile) ? s_mask[lane] : 0u;
-			const size_t at = header_words + size_t(gt) * kWarpsPerTile + lane;
-			if (lane < kWarpsPerTile)
-				for (int q = 0; q < rec.n; ++q) rec.ptr[q][at] = word;
-			const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(word));
+			// lane l carries mask word l % 8 to record target l / 8 (+ 4 in a second round): own copy and up to 7 peers
+			const uint32_t word = s_mask[lane & 7];
+			const size_t at = header_words + size_t(gt) * kWarpsPerTile + (lane & 7);
+			const int q0 = lane >> 3;
+			if (q0 < rec.n) rec.ptr[q0][at] = word;
+			if (q0 + 4 < rec.n) rec.ptr[q0 + 4][at] = word;
+			const uint32_t cnt = __reduce_add_sync(0xffffffffu, (lane < kWarpsPerTile) ? __popc(word) : 0u);
 			if (lane == 0) atomicAdd(chunk_total + gt / kChunkTiles, cnt);
 		}
 	}
@@ -610,10 +617,10 @@ constexpr int kExpandWarps = 8 * kExpandChunks;   // one 4-tile group per warp
 // three take 16.5 us (round 1: 20): the per-record cost above that is the stream of 16k mostly empty
 // warps per record through the SMs.
 //
-// Signalled form (flags != nullptr): lane 0 waits — ld.acquire.sys, bounded — for the flag of the
-// record's owner.  If the flag does not arrive within the timeout the record is NOT expanded: 1 + r
-// goes to *status (first failure wins), counts[r] becomes 0, so a half-written record never reaches
-// the scatter.  `abort_status` (plain form after zn_scene_wait_flags): a non-zero word there means
+// Signalled form (flags != nullptr): thread 0 of the CTA waits — ld.acquire.sys, bounded — for the
+// flag of the record's owner.  If the flag does not arrive within the timeout the record is NOT
+// expanded: 1 + r goes to *status (first failure wins), counts[r] becomes 0, so a half-written
+// record never reaches the scatter.  `abort_status` (plain form after zn_scene_wait_flags): a non-zero word there means
 // that wait failed; nothing is expanded and all counts are zeroed.
 __global__ void __launch_bounds__(kExpandWarps * 32)
 expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
@@ -642,8 +649,11 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 		return;
 	}
 	if (flags) {
-		uint32_t ok = 1u;
-		if (lane == 0) {
+		// ONE acquire per CTA (thread 0; bar.sync extends it to the CTA): ld.acquire.sys is LDG.STRONG.SYS +
+		// CCTL.IVALL in SASS — it invalidates the SM's L1, which the header loads below want to hit
+		__shared__ uint32_t s_ok;
+		if (threadIdx.x == 0) {
+			uint32_t ok = 1u;
 			const uint32_t* f = flags + size_t(r / records_per_flag) * flag_stride;
 			const uint64_t t0 = global_timer_ns();
 			while (int32_t(ld_acquire_sys(f) - expected) < 0) {
@@ -655,9 +665,10 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 				}
 				__nanosleep(200);
 			}
+			s_ok = ok;
 		}
-		ok = __shfl_sync(0xffffffffu, ok, 0);     // also extends lane 0's acquire to the warp
-		if (!ok) {
+		__syncthreads();
+		if (!s_ok) {
 			if (first && lane == 0) counts[r] = 0u;
 			return;
 		}
