@@ -425,10 +425,17 @@ def expand_probe(rig: Rig, scene, E: int, visible: int, records: int = 7, reps: 
     for _ in range(3):
         view.fill_(1)
     fill_us = rig.timed(lambda: view.fill_(1), reps) / reps * 1e3
+    scene.SetExpandMode(True)                   # the two-launch form: classification + work list (ZN_EXPAND_WORKLIST)
+    for _ in range(3):
+        call()
+    us_wl = rig.timed(call, reps) / reps * 1e3
+    assert counts.tolist() == [visible] * records
+    scene.SetExpandMode(False)
     scene.BindVisibilityRecord(None)
     del recs, lists
     return {"records": records, "expand_us": us, "list_write_GBs": records * visible * 4 / (us * 1e-6) / 1e9,
-            "fill_same_bytes_us": fill_us, "frac_of_fill": fill_us / us}
+            "fill_same_bytes_us": fill_us, "frac_of_fill": fill_us / us,
+            "worklist_expand_us": us_wl, "worklist_frac_of_fill": fill_us / us_wl}
 
 
 def secondary_lines(rig: Rig, scene, E: int, roots: int, steps: int, peak: float, flat_too: bool) -> list:

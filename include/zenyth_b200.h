@@ -189,6 +189,19 @@ int zn_scene_expand_visible_signalled(zn_scene* scene, const void* records_dev, 
                                       int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev, uint32_t list_stride, void* counts_dev,
                                       const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag, uint32_t expected,
                                       uint32_t timeout_ms, void* status_dev);
+/* How zn_scene_expand_visible(_signalled) and zn_exchange_expand expand records with this scene:
+ *   ZN_EXPAND_GRID (default)  one launch, one warp per 4-tile group of every record: best when most groups are
+ *                             non-empty (headline camera, f = 0.86: 64 us for seven 16.7M-entity records; 80 us with
+ *                             the work list);
+ *   ZN_EXPAND_WORKLIST        two launches chained programmatically: a classification pass (one THREAD per group)
+ *                             appends the non-empty groups to a work list, a persistent grid works it off — no warp
+ *                             is ever spent on an empty group: best for sparse visible sets (camera inside the scene,
+ *                             f = 0.21, 70% of the chunks empty: 26 us against 36 us).
+ * The lists are identical either way.  The engine knows which kind of view it renders; the library cannot know the
+ * visible fraction on the host without a synchronising read-back. */
+#define ZN_EXPAND_GRID 0
+#define ZN_EXPAND_WORKLIST 1
+int zn_scene_set_expand_mode(zn_scene* scene, int mode);
 /* Added to every index written to the visible list (shard -> global numbering). */
 int zn_scene_set_index_base(zn_scene* scene, uint32_t index_base);
 

@@ -207,6 +207,9 @@ public:
 		detail::Check(zn_scene_set_camera(m_scene, camera.View().m, camera.Proj().m), "Scene::SetCamera");
 	}
 	void SetIndexBase(uint32_t base) { detail::Check(zn_scene_set_index_base(m_scene, base), "Scene::SetIndexBase"); }
+	// Record expansion strategy (multi-GPU): a warp per group (default, dense visible sets) or classification + work
+	// list (sparse visible sets: a camera inside the scene).
+	void SetExpandWorkList(bool on) { detail::Check(zn_scene_set_expand_mode(m_scene, on ? ZN_EXPAND_WORKLIST : ZN_EXPAND_GRID), "Scene::SetExpandWorkList"); }
 
 	// One frame, asynchronous: world matrices over the hierarchy, MVP, visible list (the fused form,
 	// for the camera of SetCamera; a scene without a camera runs UpdateWorld instead).

@@ -186,6 +186,7 @@ def test_tile_tickets_wrap_around_2_to_the_32(oracle, gpu_ctx):
         else:
             sc.Update()
         rec = sc.DeviceBuffers().visibility_record
+        sc.SetExpandMode(frame % 3 == 2)                    # both expansion strategies
         sc.ExpandVisible(rec, 1, words, lists.data_ptr(), E, counts.data_ptr(), index_bases=[9])
         assert np.array_equal(sc.Visible(), ref["visible"]), frame
         assert counts[0].item() == ref["visible"].size

@@ -39,10 +39,12 @@ def _big_scene(gpu_ctx):
     return sc, sum(sizes), sc.Visible()      # the plain path is checked against the oracle elsewhere
 
 
+@pytest.mark.parametrize("worklist", [False, True], ids=["expand-grid", "expand-worklist"])
 @pytest.mark.parametrize("big", [False, True], ids=["small-levels-only", "with-a-big-level"])
-def test_kernels_store_the_record_into_every_target_and_signal(oracle, gpu_ctx, big):
+def test_kernels_store_the_record_into_every_target_and_signal(oracle, gpu_ctx, big, worklist):
     import torch
     sc, E, expect = _big_scene(gpu_ctx) if big else _scene(oracle, gpu_ctx)
+    sc.SetExpandMode(worklist)
     assert 0 < expect.size < E
     words = sc.DeviceBuffers().visibility_record_words
     recs = torch.zeros(4 * words, dtype=torch.int32, device="cuda")          # own + 3 "peers"
@@ -79,9 +81,11 @@ def test_kernels_store_the_record_into_every_target_and_signal(oracle, gpu_ctx, 
     sc.Close()
 
 
-def test_a_signal_that_never_comes_times_out_instead_of_hanging(oracle, gpu_ctx):
+@pytest.mark.parametrize("worklist", [False, True], ids=["expand-grid", "expand-worklist"])
+def test_a_signal_that_never_comes_times_out_instead_of_hanging(oracle, gpu_ctx, worklist):
     import torch
     sc, E, expect = _scene(oracle, gpu_ctx, levels=3)
+    sc.SetExpandMode(worklist)
     words = sc.DeviceBuffers().visibility_record_words
     recs = torch.zeros(2 * words, dtype=torch.int32, device="cuda")
     flags = torch.zeros(2 * 32, dtype=torch.int32, device="cuda")

@@ -111,6 +111,12 @@ struct zn_scene {
 	CUtensorMap tm_world_all, tm_mvp_all;  // all E rows (the cull pass is one launch over every level)
 	std::vector<std::pair<void*, CUtensorMap>> mvp_maps;   // tensor maps of caller-owned MVP arrays (zn_scene_cull)
 	const void* abort_status = nullptr;    // status word of the last zn_scene_wait_flags, consumed by the next plain expansion
+	uint4* expand_entries = nullptr;       // work list of the two-launch expansion: non-empty groups of the records being expanded
+	uint32_t expand_capacity = 0;
+	uint32_t* expand_count = nullptr;      // [2] by launch parity
+	uint32_t expand_parity = 0;
+	int max_ctas_expand = 0;               // co-resident CTAs of expand_work_kernel
+	int expand_mode = 0;                   // ZN_EXPAND_GRID / ZN_EXPAND_WORKLIST (zn_scene_set_expand_mode)
 	cudaEvent_t cull_events[3] = {nullptr, nullptr, nullptr};   // profiling: before cull, after cull, after emit
 	uint32_t* host_count = nullptr;      // pinned [1]
 	bool profiling = false;

@@ -4,6 +4,8 @@
 // frame calls.  The kernels live in zn_scene_kernels.cuh.
 #include "zn_scene_kernels.cuh"
 
+#include <cstdlib>
+
 namespace zn {
 
 static int ensure_staging(zn_ctx* ctx, size_t bytes) {
@@ -192,7 +194,7 @@ int zn_scene_destroy(zn_scene* s) {
 	cudaSetDevice(s->ctx->device);
 	cudaStreamSynchronize(s->ctx->stream);
 	cudaFree(s->blocks); cudaFree(s->tile_prange); cudaFree(s->world); cudaFree(s->mvp); cudaFree(s->visible_own);
-	cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->level_ticket); cudaFree(s->record_own); cudaFree(s->tile_first_entity);
+	cudaFree(s->expand_entries); cudaFree(s->expand_count); cudaFree(s->visible_count_own); cudaFree(s->chunk_total); cudaFree(s->level_ticket); cudaFree(s->record_own); cudaFree(s->tile_first_entity);
 	if (s->host_count) cudaFreeHost(s->host_count);
 	for (auto e : s->prof_events) cudaEventDestroy(e);
 	for (auto e : s->cull_events) if (e) cudaEventDestroy(e);
@@ -347,8 +349,49 @@ int zn::expand_visible_on(cudaStream_t stream, zn_scene* s, const char* who, con
 		for (uint32_t* flag : s->peer_flags) sig.flag[sig.n++] = flag;
 		sig.value = s->signal_value;
 	}
-	// One CTA per (record, chunk), one warp per 4-tile group.
 	if (record_count == skip_count && !flags_dev) return ZN_OK;     // nothing to expand and nothing to signal
+	if (s->expand_mode == ZN_EXPAND_WORKLIST) {
+		// Two launches: classify every (record, group) into a work list of the non-empty ones, then a persistent grid works it off.
+		const uint32_t live = record_count - skip_count;
+		const uint32_t groups = s->chunk_count * 8u;
+		const uint32_t need = std::max<uint32_t>(1u, live) * groups;
+		if (s->expand_capacity < need) {
+			ZN_CUDA(cudaStreamSynchronize(stream));
+			if (s->expand_entries) ZN_CUDA(cudaFree(s->expand_entries));
+			s->expand_entries = nullptr; s->expand_capacity = 0;
+			ZN_CUDA(cudaMalloc(&s->expand_entries, size_t(need) * sizeof(uint4)));
+			s->expand_capacity = need;
+		}
+		if (!s->expand_count) {
+			ZN_CUDA(cudaMalloc(&s->expand_count, 8));
+			ZN_CUDA(cudaMemsetAsync(s->expand_count, 0, 8, stream));
+			int per_sm = 0;
+			ZN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_work_kernel, kExpandWarps * 32, 0));
+			s->max_ctas_expand = std::max(per_sm, 1) * s->ctx->sm_count;
+		}
+		ExpandWork work = {s->expand_entries, s->expand_count, s->expand_parity};
+		s->expand_parity ^= 1u;
+		const dim3 cgrid((groups + kClassifyThreads - 1) / kClassifyThreads, std::max<uint32_t>(1u, live));
+		expand_classify_kernel<<<cgrid, kClassifyThreads, 0, stream>>>(
+			static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count,
+			skip_index, int(skip_count), static_cast<uint32_t*>(counts_dev), static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag,
+			uint64_t(timeout_ms) * 1000000ull, static_cast<uint32_t*>(status_dev), static_cast<const uint32_t*>(abort_status), sig, work);
+		ZN_CUDA(cudaGetLastError());
+		cudaLaunchAttribute pdl;
+		pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		pdl.val.programmaticStreamSerializationAllowed = 1;
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(std::min<uint32_t>((need + kExpandWarps - 1) / kExpandWarps, uint32_t(s->max_ctas_expand)));
+		cfg.blockDim = dim3(kExpandWarps * 32);
+		cfg.stream = stream;
+		cfg.attrs = &pdl;
+		cfg.numAttrs = 1;
+		ZN_CUDA(cudaLaunchKernelEx(&cfg, expand_work_kernel, static_cast<const uint32_t*>(records_dev), record_stride_words,
+		                           (const uint32_t*)s->tile_first_entity, s->tile_count, s->chunk_count, bases, static_cast<uint32_t*>(lists_dev),
+		                           list_stride, work));
+		return ZN_OK;
+	}
+	// One CTA per (record, chunk), one warp per 4-tile group.
 	const dim3 grid((s->chunk_count + kExpandChunks - 1) / kExpandChunks, std::max<uint32_t>(1u, record_count - skip_count));
 	expand_visible_kernel<<<grid, kExpandWarps * 32, 0, stream>>>(
 		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count,
@@ -393,6 +436,13 @@ int zn_scene_wait_flags(zn_scene* s, const void* flags_dev, uint32_t flag_stride
 	                                                uint64_t(timeout_ms) * 1000000ull, static_cast<uint32_t*>(status_dev), sig);
 	ZN_CUDA(cudaGetLastError());
 	s->abort_status = status_dev;
+	return ZN_OK;
+}
+
+int zn_scene_set_expand_mode(zn_scene* s, int mode) {
+	ZN_REQUIRE(s, "zn_scene_set_expand_mode: scene is NULL");
+	ZN_REQUIRE(mode == ZN_EXPAND_GRID || mode == ZN_EXPAND_WORKLIST, "zn_scene_set_expand_mode: unknown mode %d", mode);
+	s->expand_mode = mode;
 	return ZN_OK;
 }
 

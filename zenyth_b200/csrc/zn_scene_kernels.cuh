@@ -717,6 +717,154 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 	                   (1u << lane) - 1u, visible);
 }
 
+// ---- the expansion as two launches: classify, then work only where there is work ---------------------
+// expand_classify_kernel: one THREAD per (record, 4-tile group).  It reads the group's four header words
+// (coalesced across the CTA), and every non-empty group is appended to a work list as
+// {record << 26 | full << 25 | group, list position} — one global atomicAdd per CTA (a block scan
+// places the entries).  115k groups of seven records are 448 CTAs instead of 115k warps.
+// expand_work_kernel: a persistent grid of autonomous warps walks the work list with a static stride,
+// the next entry in flight while the current one is handled: a full group is one run of 1024
+// consecutive indices, a mixed group fetches its 32 mask words, scans and scatters.  No warp is ever
+// spent on an empty group, and consecutive entries go to different warps, so a run of mixed chunks
+// spreads over the whole GPU.  The two launches are chained with programmatic dependent launch; the
+// list's counter is double-buffered by launch parity (the work kernel clears the other one).
+constexpr int kClassifyThreads = 256;
+struct ExpandWork {
+	uint4* entries;        // [capacity]: {record << 26 | full << 25 | group, list position, first entity index (+ index base) of the group, -}
+	uint32_t* count;       // [2], by launch parity
+	uint32_t parity;
+};
+
+__global__ void __launch_bounds__(kClassifyThreads)
+expand_classify_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
+                       uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases,
+                       uint32_t record_count, int skip, int skip_count, uint32_t* __restrict__ counts,
+                       const uint32_t* __restrict__ flags, uint32_t flag_stride, uint32_t expected, uint32_t records_per_flag,
+                       uint64_t timeout_ns, uint32_t* __restrict__ status, const uint32_t* __restrict__ abort_status,
+                       const __grid_constant__ SignalTargets sig, const __grid_constant__ ExpandWork work) {
+	__shared__ uint32_t s_warp[kClassifyThreads / 32];
+	__shared__ uint32_t s_slot, s_ok;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	if (sig.n > 0 && blockIdx.x == 0 && blockIdx.y == 0 && t == 0) {
+		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank
+		raise_flags(sig);
+	}
+	if (t == 0) grid_dep_launch();                               // the work kernel may start its prologue
+	uint32_t r = blockIdx.y;                                         // one grid row per expanded record
+	if (int(r) >= skip) r += uint32_t(skip_count);
+	if (r >= record_count) return;                                   // every record skipped: this launch only signals
+	const bool first = blockIdx.x == 0 && t == 0;
+	if (t == 0) {
+		uint32_t ok = 1u;
+		if (abort_status && __ldcg(abort_status) != 0u) ok = 0u;
+		if (ok && flags) {
+			const uint32_t* f = flags + size_t(r / records_per_flag) * flag_stride;
+			const uint64_t t0 = global_timer_ns();
+			while (int32_t(ld_acquire_sys(f) - expected) < 0) {
+				if (*reinterpret_cast<volatile uint32_t*>(status) == 1u + r || global_timer_ns() - t0 > timeout_ns) {
+					atomicCAS(status, 0u, 1u + r);
+					ok = 0u;
+					break;
+				}
+				__nanosleep(200);
+			}
+		}
+		s_ok = ok;
+	}
+	__syncthreads();
+	if (!s_ok) {
+		if (first) counts[r] = 0u;
+		return;
+	}
+	const uint32_t* rec = records + size_t(r) * record_stride;
+	if (first) counts[r] = rec[chunks];
+	const uint32_t group = blockIdx.x * kClassifyThreads + t;
+	const uint32_t chunk = group >> 3;
+	uint32_t gcount = 0u, position = 0u, first_entity = 0u;
+	if (group < chunks * 8u && group * 4u < tiles) {
+		first_entity = __ldg(tile_first_entity + group * 4u) + bases.base[r];
+		const uint32_t chunk_base = rec[chunk];
+		const uint32_t chunk_count = rec[chunk + 1u] - chunk_base;
+		const uint32_t group_off = rec[chunks + 1u + group];
+		const uint32_t group_end = ((group & 7u) < 7u) ? rec[chunks + 2u + group] : chunk_count;
+		gcount = group_end - group_off;
+		if (chunk_count > uint32_t(kChunkTiles * kTile) || gcount > 4u * kTile) gcount = 0u;   // not a record: expand nothing
+		position = chunk_base + group_off;
+	}
+	// block scan of the non-empty flags -> slot of every entry, one global atomic per CTA
+	const uint32_t mine = gcount != 0u ? 1u : 0u;
+	const uint32_t ballot = __ballot_sync(0xffffffffu, mine);
+	if (lane == 0) s_warp[warp] = __popc(ballot);
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t v = (lane < kClassifyThreads / 32) ? s_warp[lane] : 0u;
+		uint32_t incl = v;
+#pragma unroll
+		for (int d = 1; d < kClassifyThreads / 32; d <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= d) incl += y;
+		}
+		if (lane < kClassifyThreads / 32) s_warp[lane] = incl - v;
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, kClassifyThreads / 32 - 1);
+		if (lane == 0) s_slot = total ? atomicAdd(work.count + work.parity, total) : 0u;
+	}
+	__syncthreads();
+	if (mine) {
+		const uint32_t slot = s_slot + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
+		work.entries[slot] = make_uint4((r << 26) | (gcount == 4u * kTile ? (1u << 25) : 0u) | group, position, first_entity, 0u);
+	}
+}
+
+__global__ void __launch_bounds__(kExpandWarps * 32)
+expand_work_kernel(const uint32_t* __restrict__ records, uint32_t record_stride, const uint32_t* __restrict__ tile_first_entity,
+                   uint32_t tiles, uint32_t chunks, const __grid_constant__ ExpandBases bases, uint32_t* __restrict__ lists,
+                   uint32_t list_stride, const __grid_constant__ ExpandWork work) {
+	__shared__ __align__(16) uint32_t s_word[kExpandWarps][32];
+	__shared__ __align__(16) uint32_t s_off[kExpandWarps][32];
+	__shared__ uint32_t s_first[kExpandWarps][4];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t workers = gridDim.x * kExpandWarps;
+	const uint32_t worker = blockIdx.x * kExpandWarps + warp;
+	const uint32_t lt = (1u << lane) - 1u;
+	grid_dep_wait();                                                 // the classification is complete and visible
+	const uint32_t n = __ldcg(work.count + work.parity);
+	if (blockIdx.x == 0 && threadIdx.x == 0) work.count[work.parity ^ 1u] = 0u;   // last read by the previous launch pair
+	if (worker >= n) return;
+	// two entries ahead of the one being handled: a full group needs nothing but its entry
+	const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+	uint4 cur = __ldcg(work.entries + worker);
+	uint4 nxt = (worker + workers < n) ? __ldcg(work.entries + worker + workers) : none;
+	for (uint32_t i = worker; i < n; i += workers) {
+		const uint32_t i2 = i + 2u * workers;
+		const uint4 nxt2 = (i2 < n) ? __ldcg(work.entries + i2) : none;
+		const uint32_t r = cur.x >> 26, group = cur.x & 0x1FFFFFFu;
+		uint32_t* visible = lists + size_t(r) * list_stride;
+		if (cur.x & (1u << 25)) {
+			store_run_1024(visible + cur.y, cur.z, lane);
+		} else {
+			const uint32_t tile = group * 4u + (lane >> 3);
+			const uint32_t* rec = records + size_t(r) * record_stride;
+			const uint32_t word = (tile < tiles) ? __ldcg(rec + record_header_words(chunks) + size_t(tile) * kWarpsPerTile + (lane & 7)) : 0u;
+			const uint32_t tfirst = (tile < tiles) ? __ldg(tile_first_entity + tile) + bases.base[r] : 0u;
+			const uint32_t cnt = __popc(word);
+			uint32_t incl = cnt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+				if (lane >= d) incl += y;
+			}
+			__syncwarp();
+			s_word[warp][lane] = word;
+			s_off[warp][lane] = cur.y + incl - cnt;
+			if ((lane & 7) == 0) s_first[warp][lane >> 3] = tfirst;
+			__syncwarp();
+			scatter_warp_words(reinterpret_cast<const uint4*>(s_word[warp]), reinterpret_cast<const uint4*>(s_off[warp]), s_first[warp], lane, lt, visible);
+		}
+		cur = nxt;
+		nxt = nxt2;
+	}
+}
+
 // Visible list -> what a draw submission consumes: the MVP matrices of the
 // visible entities packed in list order, and one indexed-indirect argument record in the
 // D3D12_DRAW_INDEXED_ARGUMENTS layout {IndexCountPerInstance, InstanceCount, StartIndexLocation,

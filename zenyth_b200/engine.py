@@ -309,6 +309,11 @@ class Scene:
             list_stride, C.c_void_p(counts_ptr), C.c_void_p(flags_ptr), flag_stride_words, records_per_flag, expected & 0xFFFFFFFF,
             timeout_ms, C.c_void_p(status_ptr)))
 
+    def SetExpandMode(self, worklist: bool) -> None:
+        """How records are expanded with this scene: one launch with a warp per group (default; dense visible sets)
+        or classification + work list (sparse visible sets).  zn_scene_set_expand_mode."""
+        check(self._lib.zn_scene_set_expand_mode(self._h, 1 if worklist else 0))
+
     def SetIndexBase(self, base: int) -> None:
         check(self._lib.zn_scene_set_index_base(self._h, base))
 
