@@ -131,3 +131,40 @@ def test_mesh_file_round_trip(oracle, gpu_ctx, tmp_path):
             zn.Mesh.LoadFile(gpu_ctx, p)
     with pytest.raises(zn.ZenythError):
         zn.Mesh.LoadFile(gpu_ctx, tmp_path / "missing.znmesh")
+
+
+@pytest.mark.parametrize("verts", [1024, 40], ids=["one-instance-per-tile", "many-instances-per-tile"])
+def test_model_matrices_that_are_not_plain_affine(oracle, gpu_ctx, verts):
+    """The kernels fold the general 4x4 inverse for affine models (bottom row exactly 0,0,0,1, moderate finite
+    entries) — results must stay equal to the oracle's GENERAL inverse bit for bit, and every model that does
+    not qualify (projective bottom row, huge entries whose products overflow, an infinity, a NaN, w != 1) must
+    take the general routine and propagate exactly what the oracle propagates."""
+    import zenyth_b200 as zn
+    rng = np.random.default_rng(31)
+    base = models_from_scene(oracle, 24).copy()
+    models = base.copy()
+    models[1] = rng.uniform(-2, 2, 16).astype(np.float32)                 # general projective matrix
+    models[2, 3] = 0.25                                                    # bottom row (0.25, 0, 0, 1)
+    models[3, 15] = 2.0                                                    # w = 2
+    models[4, 12:15] = np.float32([3e19, -2e19, 1e19])                     # huge translation: s-terms the general routine forms overflow
+    models[5, 0] = np.float32(np.inf)
+    models[6, 13] = np.float32(np.nan)
+    models[7, :] = 0.0; models[7, 15] = 1.0                                # singular affine: zero matrix by C9
+    models[8, 0:3] = np.float32([1e-30, 0, 0])                             # nearly singular, tiny determinant
+    models[9, 12:15] = np.float32([1e17, 1e17, -1e17])                     # large but still on the folded path
+    I = models.shape[0]
+    V = I * verts
+    pos, nrm = oracle.synth_mesh(BASE_SEED + 6, V)
+    first = (np.arange(I + 1, dtype=np.uint32) * verts).astype(np.uint32)
+    ref_p, ref_n = oracle.mesh_transform(first, models, pos, nrm)
+    m = zn.Mesh(gpu_ctx, V, I)
+    m.SetVertices(pos, nrm)
+    m.SetModels(models)
+    m.Transform()
+    got_p, got_n = m.Read()
+    m.Close()
+    for k in range(I):
+        sl = slice(k * verts, (k + 1) * verts)
+        assert np.array_equal(got_p[sl], ref_p[sl], equal_nan=True), f"positions of instance {k}"
+        assert np.array_equal(got_n[sl], ref_n[sl], equal_nan=True), f"normals of instance {k}"
+    assert np.isnan(ref_n[6 * verts:7 * verts]).any() or np.isnan(ref_p[6 * verts:7 * verts]).any()   # the NaN really propagates

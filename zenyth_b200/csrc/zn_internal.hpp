@@ -75,7 +75,6 @@ struct zn_scene {
 	int max_ctas_world = 0;        // ... of its world-only form (5 per SM: no MVP tile in shared memory)
 	bool has_camera = false;
 	bool world_valid = false;      // an update has run: the world matrices exist (zn_scene_cull needs them)
-	bool last_update_had_view = false;
 	bool ranges_dirty = true;      // tile_prange must be rebuilt before the next update
 	bool inputs_touched = true;    // an upload / fill has written the input blocks since the last update: level 0 must not
 	                               // start its first block load early (programmatic launch) behind the kernel that wrote them

@@ -174,4 +174,45 @@ __device__ __forceinline__ void mat4_inverse(const float* __restrict__ d, float*
 	out[12] = b03; out[13] = b13; out[14] = b23; out[15] = b33;
 }
 
+// The upper-left 3x3 of mat4_inverse(d) for an AFFINE matrix — bottom row exactly (0, 0, 0, 1), every
+// other entry finite — which is what a scene's world matrices are.  Not another algorithm: it is
+// mat4_inverse with the operations that IEEE arithmetic makes exact under those conditions folded
+// away (x*1 = x, x*0 = +-0, y + +-0 = y, y - +-0 = y), so every result equals the general routine's
+// bit for bit (up to the sign of a zero).  c5 = a22, c4 = a21, c2 = a20, c3 = c1 = c0 = +-0; of the
+// s-terms only s0, s1, s3 are needed; det = (s0*a22 - s1*a21) + s3*a20.  ~45 operations instead of
+// ~170.  Returns false (and computes nothing) when the matrix does not qualify.
+// inv3[r*3 + c] = inverse(r, c) for r, c < 3.
+__device__ __forceinline__ bool mat4_inverse_affine3x3(const float* __restrict__ d, float* __restrict__ inv3) {
+	const float a00 = d[0], a10 = d[1], a20 = d[2];
+	const float a01 = d[4], a11 = d[5], a21 = d[6];
+	const float a02 = d[8], a12 = d[9], a22 = d[10];
+	const float a03 = d[12], a13 = d[13], a23 = d[14];
+	if (!(d[3] == 0.0f && d[7] == 0.0f && d[11] == 0.0f && d[15] == 1.0f)) return false;
+	const float mag = fabsf(a00) + fabsf(a10) + fabsf(a20) + fabsf(a01) + fabsf(a11) + fabsf(a21) + fabsf(a02) + fabsf(a12) + fabsf(a22) +
+	                  fabsf(a03) + fabsf(a13) + fabsf(a23);
+	// An infinity or a NaN somewhere, or entries so large that a product the general routine forms (and then multiplies
+	// by an exact zero) could overflow: the general routine propagates NaNs there, so it has to run.
+	if (!(mag < 1.0e18f)) return false;
+	const float s0 = sub(mul(a00, a11), mul(a10, a01));
+	const float s1 = sub(mul(a00, a12), mul(a10, a02));
+	const float s3 = sub(mul(a01, a12), mul(a11, a02));
+	const float det = add(sub(mul(s0, a22), mul(s1, a21)), mul(s3, a20));
+	if (det == 0.0f) {
+#pragma unroll
+		for (int i = 0; i < 9; ++i) inv3[i] = 0.0f;
+		return true;
+	}
+	const float inv = __fdiv_rn(1.0f, det);
+	inv3[0] = mul(sub(mul(a11, a22), mul(a12, a21)), inv);   // b00
+	inv3[1] = mul(sub(mul(a02, a21), mul(a01, a22)), inv);   // b01
+	inv3[2] = mul(s3, inv);                                  // b02
+	inv3[3] = mul(sub(mul(a12, a20), mul(a10, a22)), inv);   // b10
+	inv3[4] = mul(sub(mul(a00, a22), mul(a02, a20)), inv);   // b11
+	inv3[5] = mul(sub(0.0f, s1), inv);                       // b12
+	inv3[6] = mul(sub(mul(a10, a21), mul(a11, a20)), inv);   // b20
+	inv3[7] = mul(sub(mul(a01, a20), mul(a00, a21)), inv);   // b21
+	inv3[8] = mul(s0, inv);                                  // b22
+	return true;
+}
+
 } // namespace zn

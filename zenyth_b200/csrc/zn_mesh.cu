@@ -34,25 +34,46 @@ constexpr uint32_t kMeshSmemMats = 1024;       // most instances of one tile who
 constexpr int kSmemMatFloats = 21;             // rows 0..2 of the model (12) + 3x3 normal matrix (9); odd stride: conflict-free
 constexpr int kInstMatFloats = 24;             // the same in global memory (tiles with > kMeshSmemMats instances), padded to 16 bytes
 
+// N[r*3 + c] = ((model^-1)^T)(r, c) = inverse(c, r), r, c < 3.  A scene's world matrices are affine (bottom row exactly
+// 0,0,0,1): for those the general 4x4 inverse folds to ~45 operations with bit-identical results
+// (mat4_inverse_affine3x3); anything else — a projective model, an infinity — takes the general routine.
+__device__ __forceinline__ void normal_matrix(const float* __restrict__ m, float* __restrict__ N) {
+	float inv3[9];
+	if (mat4_inverse_affine3x3(m, inv3)) {
+#pragma unroll
+		for (int r = 0; r < 3; ++r)
+#pragma unroll
+			for (int c = 0; c < 3; ++c) N[r * 3 + c] = inv3[c * 3 + r];
+		return;
+	}
+	float inv[16];
+	mat4_inverse(m, inv);
+#pragma unroll
+	for (int r = 0; r < 3; ++r)
+#pragma unroll
+		for (int c = 0; c < 3; ++c) N[r * 3 + c] = inv[r * 4 + c];   // transpose(inverse)(r,c) = inverse(c,r)
+}
+
 // Per-instance matrices for tiles that span several instances.
 __global__ void mesh_instance_mats_kernel(const float* __restrict__ models, uint32_t instances, float* __restrict__ out) {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= instances) return;
-	float m[16], inv[16];
+	float m[16];
 	const float4* src = reinterpret_cast<const float4*>(models + size_t(k) * 16);
 #pragma unroll
 	for (int c = 0; c < 4; ++c) {
 		const float4 col = __ldg(src + c);
 		m[c * 4 + 0] = col.x; m[c * 4 + 1] = col.y; m[c * 4 + 2] = col.z; m[c * 4 + 3] = col.w;
 	}
-	mat4_inverse(m, inv);
 	float* o = out + size_t(k) * kInstMatFloats;
+	float N[9];
+	normal_matrix(m, N);
 #pragma unroll
 	for (int r = 0; r < 3; ++r) {
 #pragma unroll
 		for (int c = 0; c < 4; ++c) o[r * 4 + c] = m[c * 4 + r];
 #pragma unroll
-		for (int c = 0; c < 3; ++c) o[12 + r * 3 + c] = inv[r * 4 + c];   // transpose(inverse)(r,c) = inverse(c,r)
+		for (int c = 0; c < 3; ++c) o[12 + r * 3 + c] = N[r * 3 + c];
 	}
 }
 
@@ -100,17 +121,14 @@ mesh_tile_kernel(const zn_mesh_tile* __restrict__ tiles, const float* __restrict
 
 	// Model rows + normal matrix of one instance: M[r*4+c] = model(r,c), N[r*3+c] = inverse(c,r).
 	auto instance_matrices = [&](const float4* col, float* M, float* N) {
-		float m[16], inv[16];
+		float m[16];
 #pragma unroll
 		for (int c = 0; c < 4; ++c) { m[c * 4 + 0] = col[c].x; m[c * 4 + 1] = col[c].y; m[c * 4 + 2] = col[c].z; m[c * 4 + 3] = col[c].w; }
-		mat4_inverse(m, inv);
+		normal_matrix(m, N);
 #pragma unroll
-		for (int r = 0; r < 3; ++r) {
+		for (int r = 0; r < 3; ++r)
 #pragma unroll
 			for (int c = 0; c < 4; ++c) M[r * 4 + c] = m[c * 4 + r];
-#pragma unroll
-			for (int c = 0; c < 3; ++c) N[r * 3 + c] = inv[r * 4 + c];   // transpose(inverse)(r,c) = inverse(c,r)
-		}
 	};
 
 	if (t == 0) {

@@ -550,7 +550,6 @@ static int run_update(zn_scene* s, bool with_view) {
 		if (rc != ZN_OK) return rc;
 	}
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size() + 1], ctx->stream));
-	s->last_update_had_view = with_view;
 	s->world_valid = true;
 	s->inputs_touched = false;
 	return ZN_OK;
