@@ -248,7 +248,9 @@ typedef struct zn_scene_buffers {
 	void* mvp;              /* float[E][16] */
 	void* visible;          /* uint32[E], first *visible_count entries valid, ascending */
 	void* visible_count;    /* uint32[1] */
-	void* visibility_record;          /* uint32[visibility_record_words]: the frame's visible set at 1 bit per
+	void* visibility_record;          /* (of the LAST update or cull pass — the scene's own record is double-buffered by
+	                                     frame, so ask again after every frame —)
+	                                     uint32[visibility_record_words]: the frame's visible set at 1 bit per
 	                                     entity — a header of list offsets per 8192-entity chunk and the total
 	                                     count, then 8 mask words per 256-entity tile.  Opaque: produced by
 	                                     zn_scene_update, consumed by zn_scene_expand_visible. */

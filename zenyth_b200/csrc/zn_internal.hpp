@@ -94,14 +94,18 @@ struct zn_scene {
 	// visibility record of a frame: header (chunk bases, total, group offsets; see
 	// record_header_words in zn_scene.cu), then [tiles][8] mask words
 	uint32_t* record = nullptr;            // where the kernels write (own buffer or a bound one)
-	uint32_t* record_own = nullptr;
+	uint32_t* record_own = nullptr;        // [2][record_words]: the scene's own record, double-buffered by frame so that frame k+1's
+	                                       // level kernels can write masks while frame k's emit still reads its own
+	uint32_t record_slot = 0;
+	bool tail_is_emit = false;             // the last kernel this scene launched was an emit: every level kernel before it has completed
+	bool record_bound = false;             // zn_scene_bind_visibility_record: caller-owned memory, one buffer, no frame overlap
 	uint32_t record_words = 0;
 	std::vector<uint32_t*> peer_records;   // copies of the record kept by peer GPUs (mapped device pointers), written by the kernels
 	std::vector<uint32_t*> peer_flags;     // one flag word per rank (own included), raised to signal_value by zn_scene_expand_visible_signalled
 	uint32_t signal_value = 0;
 	uint32_t* tile_first_entity = nullptr; // [tiles]
 	uint32_t chunk_count = 0;              // emit CTAs: 32 tiles each
-	uint32_t* chunk_total = nullptr;       // [2][chunks] visible count per chunk, one set per frame parity
+	uint32_t* chunk_total = nullptr;       // [3][chunks] visible count per chunk: frame k accumulates into set k % 3, its emit clears set (k + 2) % 3
 	uint32_t frame_parity = 0;
 	uint32_t* level_ticket = nullptr;      // [levels + 1] monotonically increasing tickets: one counter per level, then the
 	                                       // cull pass's tile counter

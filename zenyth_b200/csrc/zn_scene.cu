@@ -156,19 +156,19 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 	ZN_TRY(cudaMalloc(&s->visible_count_own, 4));
 	s->visible = s->visible_own;
 	s->visible_count = s->visible_count_own;
-	ZN_TRY(cudaMalloc(&s->chunk_total, size_t(s->chunk_count) * 2 * 4));   // two sets, by frame parity
+	ZN_TRY(cudaMalloc(&s->chunk_total, size_t(s->chunk_count) * 3 * 4));   // three sets, by frame number mod 3
 	ZN_TRY(cudaMalloc(&s->level_ticket, (s->levels.size() + 1) * 4));
 	ZN_TRY(cudaMemsetAsync(s->level_ticket, 0, (s->levels.size() + 1) * 4, ctx->stream));
 	s->record_words = record_header_words(s->chunk_count) + s->tile_count * kWarpsPerTile;
-	ZN_TRY(cudaMalloc(&s->record_own, size_t(s->record_words) * 4));
-	ZN_TRY(cudaMemsetAsync(s->record_own, 0, size_t(s->record_words) * 4, ctx->stream));
+	ZN_TRY(cudaMalloc(&s->record_own, size_t(s->record_words) * 2 * 4));
+	ZN_TRY(cudaMemsetAsync(s->record_own, 0, size_t(s->record_words) * 2 * 4, ctx->stream));
 	s->record = s->record_own;
 	ZN_TRY(cudaMalloc(&s->tile_first_entity, size_t(s->tile_count) * 4));
 	ZN_TRY(cudaHostAlloc(&s->host_count, 4, cudaHostAllocDefault));
 	ZN_TRY(cudaMemsetAsync(s->blocks, 0, size_t(s->tile_count) * kBlockWords * 4, ctx->stream));
 	init_parent_rows_kernel<<<(s->tile_count * kTile + 255) / 256, 256, 0, ctx->stream>>>(s->blocks, s->tile_count);
 	ZN_TRY(cudaGetLastError());
-	ZN_TRY(cudaMemsetAsync(s->chunk_total, 0, size_t(s->chunk_count) * 2 * 4, ctx->stream));
+	ZN_TRY(cudaMemsetAsync(s->chunk_total, 0, size_t(s->chunk_count) * 3 * 4, ctx->stream));
 	ZN_TRY(cudaMemcpyAsync(s->tile_first_entity, tile_first.data(), tile_first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	ZN_TRY(cudaMemsetAsync(s->visible_count, 0, 4, ctx->stream));
 	ZN_TRY(cudaStreamSynchronize(ctx->stream));
@@ -293,7 +293,8 @@ int zn_scene_bind_visible_output(zn_scene* s, void* visible_dev, uint32_t capaci
 
 int zn_scene_bind_visibility_record(zn_scene* s, void* record_dev) {
 	ZN_REQUIRE(s, "zn_scene_bind_visibility_record: scene is NULL");
-	s->record = record_dev ? static_cast<uint32_t*>(record_dev) : s->record_own;
+	s->record_bound = record_dev != nullptr;
+	s->record = record_dev ? static_cast<uint32_t*>(record_dev) : s->record_own + size_t(s->record_slot) * s->record_words;
 	return ZN_OK;
 }
 
@@ -471,7 +472,19 @@ static int launch_emit(zn_scene* s, const RecordTargets& rec, const uint32_t* to
 	cfg.numAttrs = pdl_ok ? 1 : 0;
 	ZN_CUDA(cudaLaunchKernelEx(&cfg, emit_visible_kernel, rec, (const uint32_t*)s->tile_first_entity, s->tile_count, s->chunk_count,
 	                           totals, totals_next, s->index_base, visible, visible_count, remote_tiles_below));
+	s->tail_is_emit = true;
 	return ZN_OK;
+}
+
+// Next record slot (own record only) and next set of chunk totals: frame k uses totals set k % 3, its emit clears set
+// (k + 2) % 3 — the one frame k - 1 used, whose emit has completed by then (every kernel of a frame waits for the one
+// before it, level 0 at the latest when it ends).
+static void next_frame_buffers(zn_scene* s) {
+	s->frame_parity = (s->frame_parity + 1u) % 3u;
+	if (!s->record_bound) {
+		s->record_slot ^= 1u;
+		s->record = s->record_own + size_t(s->record_slot) * s->record_words;
+	}
 }
 
 static RecordTargets record_targets(const zn_scene* s) {
@@ -498,22 +511,31 @@ static int run_update(zn_scene* s, bool with_view) {
 		std::memcpy(fc.planes, s->planes, sizeof(fc.planes));
 	}
 	const bool prof = s->profiling;
-	const RecordTargets rec = record_targets(s);
 	const uint32_t header_words = record_header_words(s->chunk_count);
 	// Peers get the masks of the leading run of small levels from the emit kernel, of every other
 	// level from its level kernel (see emit_chunk).
-	RecordTargets rec_local = rec;
-	rec_local.n = 1;
 	size_t small_levels = 0;
+	const uint32_t n_targets = 1u + uint32_t(s->peer_records.size());
 	uint32_t remote_tiles_below = 0;
-	if (rec.n > 1)
+	if (n_targets > 1)
 		while (small_levels < s->levels.size() && s->levels[small_levels].tiles < kSmallLevelTiles) {
 			remote_tiles_below = s->levels[small_levels].tile_base + s->levels[small_levels].tiles;
 			++small_levels;
 		}
+	// A frame with a view takes the next record slot (own record only) and the next set of chunk totals, so that its level
+	// kernels share nothing with the previous frame's emit kernel and may run beside it.
+	if (with_view) next_frame_buffers(s);
+	const RecordTargets rec = record_targets(s);
+	RecordTargets rec_local = rec;
+	rec_local.n = 1;
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
-	uint32_t* totals_next = s->chunk_total + size_t(s->frame_parity ^ 1u) * s->chunk_count;
-	if (with_view) s->frame_parity ^= 1u;
+	uint32_t* totals_next = s->chunk_total + size_t((s->frame_parity + 2u) % 3u) * s->chunk_count;
+	// Level 0 need not wait for the kernel before it (the previous frame's emit, or whatever reads the last results) as
+	// long as it overwrites nothing that kernel uses: always true for a world-only update, true for a fused one when the
+	// record is the scene's own (double-buffered).  Not after an upload: then even the input blocks are still being written.
+	// And only behind an EMIT kernel of this scene — by then every level kernel of the previous frame has completed (a
+	// world-only update ends with a level kernel that may still be reading the parents level 0 is about to rewrite).
+	const uint32_t defer_wait = (s->tail_is_emit && !s->inputs_touched && !s->profiling && (!with_view || !s->record_bound)) ? 1u : 0u;
 	// Every kernel of a frame is launched with programmatic stream serialization: its prologue (and
 	// the first input-block load) overlaps the tail of the kernel before it; it calls
 	// griddepcontrol.wait before touching anything that kernel wrote.  That includes level 0, whose
@@ -537,7 +559,7 @@ static int run_update(zn_scene* s, bool with_view) {
 		auto launch = [&](auto kernel) {
 			return cudaLaunchKernelEx(&cfg, kernel, lv.tm_world, lv.tm_mvp, fc, (const uint32_t*)s->blocks, (const uint2*)s->tile_prange,
 			                          (const float*)s->world, lv.begin, lv.end, lv.tile_base, lv.tiles, l < small_levels ? rec_local : rec,
-			                          header_words, totals, ticket, lv.ticket_base);
+			                          header_words, totals, ticket, lv.ticket_base, l == 0 ? defer_wait : 0u);
 		};
 		if (l == 0) ZN_CUDA(with_view ? launch(scene_level_kernel<false, true>) : launch(scene_level_kernel<false, false>));
 		else ZN_CUDA(with_view ? launch(scene_level_kernel<true, true>) : launch(scene_level_kernel<true, false>));
@@ -545,6 +567,7 @@ static int run_update(zn_scene* s, bool with_view) {
 		lv.ticket_base += lv.tiles + grid;
 	}
 	if (prof) ZN_CUDA(cudaEventRecord(s->prof_events[s->levels.size()], ctx->stream));
+	s->tail_is_emit = false;
 	if (with_view) {
 		const int rc = launch_emit(s, rec, totals, totals_next, s->visible, s->visible_count, remote_tiles_below, !prof);
 		if (rc != ZN_OK) return rc;
@@ -612,10 +635,11 @@ int zn_scene_cull(zn_scene* s, const float view[16], const float proj[16], const
 	zn_mat4_mul(proj, view, vp);
 	std::memcpy(fc.vp, vp, sizeof(fc.vp));
 	zn_frustum_planes(vp, fc.planes);
+	next_frame_buffers(s);
+	s->tail_is_emit = false;
 	const RecordTargets rec = record_targets(s);
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
-	uint32_t* totals_next = s->chunk_total + size_t(s->frame_parity ^ 1u) * s->chunk_count;
-	s->frame_parity ^= 1u;
+	uint32_t* totals_next = s->chunk_total + size_t((s->frame_parity + 2u) % 3u) * s->chunk_count;
 	const bool prof = s->profiling;
 	if (prof) ZN_CUDA(cudaEventRecord(s->cull_events[0], ctx->stream));
 	const uint32_t grid = std::min<uint32_t>(s->tile_count, uint32_t(s->max_ctas_cull));

@@ -103,7 +103,7 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
                    const uint2* __restrict__ tile_prange, const float* __restrict__ world_rd,
                    uint32_t begin, uint32_t end, uint32_t tile_base, uint32_t tiles,
                    const __grid_constant__ RecordTargets rec, uint32_t header_words, uint32_t* __restrict__ chunk_total,
-                   uint32_t* __restrict__ ticket, uint32_t ticket_base) {
+                   uint32_t* __restrict__ ticket, uint32_t ticket_base, uint32_t defer_wait) {
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ uint64_t s_full;
 	__shared__ uint2 s_meta;
@@ -141,7 +141,9 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 			bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, 9u * kTile * 4u, &s_full);
 			bulk_g2s(const_cast<uint32_t*>(in_blk) + 15 * kTile, blocks + size_t(gt) * kBlockWords + 15 * kTile, kTile * 4u, &s_full);
 		}
-		if (first_tile) grid_dep_wait();   // everything from here on is ordered behind the kernel before this one on the stream
+		// everything from here on is ordered behind the kernel before this one on the stream — unless this launch touches
+		// nothing that kernel reads or writes (defer_wait: level 0 of a frame running beside the previous frame's emit)
+		if (first_tile && !defer_wait) grid_dep_wait();
 		if (staged) bulk_g2s(const_cast<float4*>(in_par), world_rd + size_t(pr.x) * 16, pr.y * 64u, &s_full);
 	};
 
@@ -252,7 +254,12 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 			if (q0 + 4 < rec.n) rec.ptr[q0 + 4][at] = word;
 		}
 	}
-	if (t == 0) bulk_wait_read_all();
+	if (t == 0) {
+		bulk_wait_read_all();
+		// defer_wait: the dependency on the kernel before this one is only one of ORDER — the kernels after this one wait
+		// for this grid to complete, and through this wait for everything before it (the previous frame's emit)
+		if (defer_wait) grid_dep_wait();
+	}
 }
 
 // scene_cull_kernel — a camera pass over world matrices that already exist (zn_scene_cull): what
