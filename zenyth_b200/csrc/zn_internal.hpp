@@ -98,6 +98,8 @@ struct zn_scene {
 	                                       // level kernels can write masks while frame k's emit still reads its own
 	uint32_t record_slot = 0;
 	bool tail_is_emit = false;             // the last kernel this scene launched was an emit: every level kernel before it has completed
+	const uint32_t* frame_record = nullptr;      // record of the last frame with a view, and of the one before it
+	const uint32_t* prev_frame_record = nullptr;
 	bool record_bound = false;             // zn_scene_bind_visibility_record: caller-owned memory, one buffer, no frame overlap
 	uint32_t record_words = 0;
 	std::vector<uint32_t*> peer_records;   // copies of the record kept by peer GPUs (mapped device pointers), written by the kernels

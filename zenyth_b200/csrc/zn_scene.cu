@@ -480,11 +480,13 @@ static int launch_emit(zn_scene* s, const RecordTargets& rec, const uint32_t* to
 // (k + 2) % 3 — the one frame k - 1 used, whose emit has completed by then (every kernel of a frame waits for the one
 // before it, level 0 at the latest when it ends).
 static void next_frame_buffers(zn_scene* s) {
+	s->prev_frame_record = s->frame_record;
 	s->frame_parity = (s->frame_parity + 1u) % 3u;
 	if (!s->record_bound) {
 		s->record_slot ^= 1u;
 		s->record = s->record_own + size_t(s->record_slot) * s->record_words;
 	}
+	s->frame_record = s->record;
 }
 
 static RecordTargets record_targets(const zn_scene* s) {
@@ -531,11 +533,12 @@ static int run_update(zn_scene* s, bool with_view) {
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
 	uint32_t* totals_next = s->chunk_total + size_t((s->frame_parity + 2u) % 3u) * s->chunk_count;
 	// Level 0 need not wait for the kernel before it (the previous frame's emit, or whatever reads the last results) as
-	// long as it overwrites nothing that kernel uses: always true for a world-only update, true for a fused one when the
-	// record is the scene's own (double-buffered).  Not after an upload: then even the input blocks are still being written.
+	// long as it overwrites nothing that kernel uses: always true for a world-only update, true for a fused one when this
+	// frame's record is not the previous frame's (the scene's own is double-buffered; an exchange binds another slot every
+	// frame).  Not after an upload: then even the input blocks are still being written.
 	// And only behind an EMIT kernel of this scene — by then every level kernel of the previous frame has completed (a
 	// world-only update ends with a level kernel that may still be reading the parents level 0 is about to rewrite).
-	const uint32_t defer_wait = (s->tail_is_emit && !s->inputs_touched && !s->profiling && (!with_view || !s->record_bound)) ? 1u : 0u;
+	const uint32_t defer_wait = (s->tail_is_emit && !s->inputs_touched && !s->profiling && (!with_view || s->frame_record != s->prev_frame_record)) ? 1u : 0u;
 	// Every kernel of a frame is launched with programmatic stream serialization: its prologue (and
 	// the first input-block load) overlaps the tail of the kernel before it; it calls
 	// griddepcontrol.wait before touching anything that kernel wrote.  That includes level 0, whose
