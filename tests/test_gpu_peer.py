@@ -39,12 +39,15 @@ def _big_scene(gpu_ctx):
     return sc, sum(sizes), sc.Visible()      # the plain path is checked against the oracle elsewhere
 
 
+@pytest.mark.parametrize("two_calls", [False, True], ids=["fused-update", "update-world+cull"])
 @pytest.mark.parametrize("worklist", [False, True], ids=["expand-grid", "expand-worklist"])
 @pytest.mark.parametrize("big", [False, True], ids=["small-levels-only", "with-a-big-level"])
-def test_kernels_store_the_record_into_every_target_and_signal(oracle, gpu_ctx, big, worklist):
+def test_kernels_store_the_record_into_every_target_and_signal(oracle, gpu_ctx, big, worklist, two_calls):
     import torch
+    import zenyth_b200 as zn
     sc, E, expect = _big_scene(gpu_ctx) if big else _scene(oracle, gpu_ctx)
     sc.SetExpandMode(worklist)
+    cam = zn.Camera(zn.CameraDesc(eye=(0.0, 0.0, 1500.0), center=(0.0, 0.0, 1499.0)))
     assert 0 < expect.size < E
     words = sc.DeviceBuffers().visibility_record_words
     recs = torch.zeros(4 * words, dtype=torch.int32, device="cuda")          # own + 3 "peers"
@@ -59,7 +62,11 @@ def test_kernels_store_the_record_into_every_target_and_signal(oracle, gpu_ctx, 
     sc.BindPeerSignal([fbase + 128 * r for r in range(4)])
     for frame in range(3):                                                    # the done-counter resets every frame
         sc.SetSignalValue(frame + 1)
-        sc.Update()
+        if two_calls:                                                         # the cull pass stores the record into the targets itself
+            sc.UpdateWorld()
+            sc.Cull(cam)
+        else:
+            sc.Update()
         sc.ExpandVisibleSignalled(base, 4, words, lists.data_ptr(), E, counts.data_ptr(), fbase, 32, frame + 1, status.data_ptr(),
                                   index_bases=[0, 0, 7, 0], timeout_ms=5000)
         gpu_ctx.Sync()

@@ -639,6 +639,8 @@ int zn_scene_cull(zn_scene* s, const float view[16], const float proj[16], const
 	std::memcpy(fc.vp, vp, sizeof(fc.vp));
 	zn_frustum_planes(vp, fc.planes);
 	next_frame_buffers(s);
+	// behind an emit kernel of this scene (a previous pass, or a fused update) the pass need not wait: see scene_cull_kernel
+	const uint32_t defer_wait = (s->tail_is_emit && !s->inputs_touched && !s->profiling && s->frame_record != s->prev_frame_record) ? 1u : 0u;
 	s->tail_is_emit = false;
 	const RecordTargets rec = record_targets(s);
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;
@@ -661,7 +663,7 @@ int zn_scene_cull(zn_scene* s, const float view[16], const float proj[16], const
 		cfg.numAttrs = (prof || s->inputs_touched) ? 0 : 1;
 		ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_cull_kernel, s->tm_world_all, *tm_mvp, fc, (const uint32_t*)s->blocks,
 		                           (const uint32_t*)s->tile_first_entity, s->tile_count, s->entity_count, rec,
-		                           record_header_words(s->chunk_count), totals, ticket, s->cull_ticket_base));
+		                           record_header_words(s->chunk_count), totals, ticket, s->cull_ticket_base, defer_wait));
 	}
 	s->cull_ticket_base += s->tile_count + grid;
 	if (prof) ZN_CUDA(cudaEventRecord(s->cull_events[1], ctx->stream));

@@ -283,7 +283,7 @@ scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_con
                   const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
                   const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t entity_count,
                   const __grid_constant__ RecordTargets rec, uint32_t header_words, uint32_t* __restrict__ chunk_total,
-                  uint32_t* __restrict__ ticket, uint32_t ticket_base) {
+                  uint32_t* __restrict__ ticket, uint32_t ticket_base, uint32_t defer_wait) {
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ uint64_t s_full;
 	__shared__ uint2 s_meta[2];      // {first entity, entities} of the tile of iteration n (slot n&1) and n+1
@@ -308,7 +308,9 @@ scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_con
 		s_meta[slot] = make_uint2(first, next - first);
 		mbar_arrive_expect_tx(&s_full, kTile * 64u + kAabbBytes);
 		bulk_g2s(const_cast<float*>(in_aabb), blocks + size_t(gt) * kBlockWords + 9 * kTile, kAabbBytes, &s_full);
-		if (first_tile) grid_dep_wait();
+		// defer_wait: the kernel before this one is an emit — the world matrices were complete before IT started, and this
+		// pass shares no buffer with it (next record slot, next set of totals) — so the two run side by side
+		if (first_tile && !defer_wait) grid_dep_wait();
 		tensor_load_2d(const_cast<float4*>(in_world), &tm_world, 0, int32_t(first), &s_full);
 	};
 
@@ -376,7 +378,10 @@ scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_con
 			if (lane == 0) atomicAdd(chunk_total + gt / kChunkTiles, cnt);
 		}
 	}
-	if (t == 0) bulk_wait_read_all();
+	if (t == 0) {
+		bulk_wait_read_all();
+		if (defer_wait) grid_dep_wait();   // keeps the chain of completions: whoever waits for this grid has waited for that emit
+	}
 }
 
 // One chunk (32 tiles = 8192 entities) of an ordered visible list: `totals` holds every chunk's
