@@ -308,9 +308,10 @@ int zn_exchange_bind(zn_exchange* x, zn_scene* const* scenes, uint32_t scene_cou
 	for (uint32_t j = 0; j < scene_count; ++j) {
 		zn_scene* sc = scenes[j];
 		ZN_REQUIRE(sc && sc->ctx == x->ctx, "zn_exchange_bind: scene %u is NULL or belongs to another context", j);
-		ZN_REQUIRE(sc->record_words <= x->record_words && sc->entity_count <= x->capacity,
-		           "zn_exchange_bind: scene %u (%u record words, %u entities) does not fit the exchange (%u, %u)", j, sc->record_words,
-		           sc->entity_count, x->record_words, x->capacity);
+		// every exchanged scene shares ONE level layout: the expansion reads all records with the layout of the scene it is given
+		ZN_REQUIRE(sc->record_words == x->record_words && sc->entity_count <= x->capacity,
+		           "zn_exchange_bind: scene %u (%u record words, %u entities) does not match the exchange (%u record words, capacity %u)", j,
+		           sc->record_words, sc->entity_count, x->record_words, x->capacity);
 		const uint32_t record = x->rank * x->per_rank + j;
 		const size_t off = slot * x->slot_bytes + size_t(record) * x->record_words * 4;
 		void* peers[8];
