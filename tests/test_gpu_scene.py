@@ -373,3 +373,52 @@ def test_scene_given_in_creation_order(oracle, gpu_ctx):
     got = run_gpu(gpu_ctx, laid_out, view, proj)
     assert same_values(got["world"], ref["world"][pick]) and same_values(got["mvp"], ref["mvp"][pick])
     assert np.array_equal(np.sort(pick[got["visible"]]), ref["visible"])
+
+
+def test_host_frames_with_ranges_and_absent_arrays(oracle, gpu_ctx):
+    """zn_frame_host_io takes NULL arrays (keep what is resident) and a (first, count) range: a frame that only
+    spins some entities uploads 12 bytes for each of them and nothing else.  Pipelined and one-at-a-time forms,
+    ranges that straddle hierarchy levels, results against the oracle on the edited inputs."""
+    import zenyth_b200 as zn
+    sizes = h8_geo_level_sizes(7, 5)
+    E = sum(sizes)
+    arrays = oracle.synth_scene(BASE_SEED + 3, sizes, fanout=8, center_range=0.25)
+    view, proj = camera(oracle)
+    sc = zn.Scene(gpu_ctx, E, arrays["level_offsets"])
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    cur = {k: v.copy() for k, v in arrays.items()}
+    vis = gpu_ctx.HostAlloc((E,), np.uint32)
+    rng = np.random.default_rng(5)
+    # (1) pipelined: rotation only, ranges that start inside one level and end inside another
+    edits = [(0, 7), (3, 500), (60, 4000), (4000, E - 4000), (0, E)]
+    bufs = [gpu_ctx.HostAlloc((E, 3), np.float32) for _ in range(2)]
+    expect = []
+    for f, (first, count) in enumerate(edits):
+        cur["rotation"][first:first + count] = rng.uniform(-3.1, 3.1, (count, 3)).astype(np.float32)
+        expect.append(oracle.scene_update(cur, view, proj)["visible"].copy())
+        if f >= 2:                                              # frame f-2 used the buffer frame f is about to fill
+            n = sc.WaitFrameHost(vis)
+            assert np.array_equal(vis[:n], expect[f - 2]), f - 2
+        b = bufs[f % 2]
+        b[:count] = cur["rotation"][first:first + count]
+        sc.SubmitFrameHost(rotation=b[:count], first=first, count=count)
+    for f in (len(edits) - 2, len(edits) - 1):
+        n = sc.WaitFrameHost(vis)
+        assert np.array_equal(vis[:n], expect[f]), f
+    assert same_values(sc.World(), oracle.scene_update(cur, view, proj)["world"])
+    # (2) one frame at a time: position only for a range, then nothing at all (a pure re-run)
+    first, count = 50, 3000
+    cur["position"][first:first + count] += np.float32([5.0, -3.0, 1.0])
+    ref = oracle.scene_update(cur, view, proj)
+    n = sc.FrameHost(position=np.ascontiguousarray(cur["position"][first:first + count]), visible=vis, first=first, count=count)
+    assert np.array_equal(vis[:n], ref["visible"]) and same_values(sc.World(), ref["world"])
+    sc.SubmitFrameHost()                                        # no array at all: just the frame
+    n = sc.WaitFrameHost(vis)
+    assert np.array_equal(vis[:n], ref["visible"])
+    back = sc.Inputs()
+    for k in ("position", "rotation", "scale"):
+        assert np.array_equal(back[k], cur[k]), k
+    with pytest.raises(zn.ZenythError):
+        sc.SubmitFrameHost(rotation=bufs[0][:10], first=E - 5, count=10)   # range past the end
+    sc.Close()
