@@ -20,6 +20,7 @@ E = sum(sizes)
 sc = zn.Scene(ctx, E, np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32))
 sc.FillSynthetic(0x5A454E59 + 3, 8, 0.0)
 sc.SetCamera(zn.Camera(zn.CameraDesc(eye=(0.0, 0.0, EYE_Z), center=(0.0, 0.0, EYE_Z - 1.0))))
+sc.SetExpandMode(os.environ.get("ZN_EXPAND_MODE", "grid") == "worklist")
 words = sc.DeviceBuffers().visibility_record_words
 recs = torch.zeros(R * words, dtype=torch.int32, device=dev)
 sc.BindVisibilityRecord(recs.data_ptr())

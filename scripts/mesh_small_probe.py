@@ -21,12 +21,14 @@ stream = torch.cuda.Stream(dev)
 torch.cuda.set_stream(stream)
 ctx = zn.GpuContext(0, stream=stream.cuda_stream)
 out = {}
-for verts, inst in ((1024, 65536), (36, 1 << 20), (8, 1 << 22), (4, 1 << 23), (3, 1 << 23)):
+for verts, inst, table in ((1024, 65536, False), (36, 1 << 20, False), (8, 1 << 22, False), (4, 1 << 23, False), (3, 1 << 23, False),
+                           (36, 1 << 20, True), (8, 1 << 22, True)):
     V = verts * inst
     scene = zn.Scene(ctx, inst)
     scene.FillSynthetic(0x5A454E59 + 2, 1, 0.0)
     scene.UpdateWorld()
-    mesh = zn.Mesh(ctx, V, inst)
+    # table=True: the same equal ranges given as an explicit instance_first_vertex array (what a ragged batch runs)
+    mesh = zn.Mesh(ctx, V, inst, (np.arange(inst + 1, dtype=np.uint64) * verts).astype(np.uint32) if table else None)
     mesh.FillSynthetic(0x5A454E59 + 4)
     mesh.BindSceneModels(scene, 0)
     for _ in range(3):
@@ -40,7 +42,7 @@ for verts, inst in ((1024, 65536), (36, 1 << 20), (8, 1 << 22), (4, 1 << 23), (3
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 20
     alg = V * 48 + inst * 64
-    out[f"{inst}x{verts}"] = {"vertices": V, "ms": ms, "G_vertices_per_s": V / (ms * 1e-3) / 1e9,
+    out[f"{inst}x{verts}" + ("/table" if table else "")] = {"vertices": V, "ms": ms, "G_vertices_per_s": V / (ms * 1e-3) / 1e9,
                               "frac_48B_per_vertex": V * 48 / (ms * 1e-3) / 1e9 / peak,
                               "frac_incl_model_matrices": alg / (ms * 1e-3) / 1e9 / peak}
     mesh.Close()

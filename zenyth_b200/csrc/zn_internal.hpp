@@ -152,6 +152,7 @@ struct zn_mesh {
 	float* inst_mats = nullptr;      // [I][24] model rows + normal matrix, only when some tile holds more instances than its shared-memory window
 	bool multi_instance_tiles = false;
 	bool needs_inst_mats = false;
+	uint32_t uniform_vpi = 0;        // vertices per instance when the ranges are equal (no boundary table reads), else 0
 	uint32_t smem_window = 0;        // most instances any multi-instance tile touches (<= 1024): sizes the kernel's dynamic shared memory
 	const float* models = nullptr;   // models_own or a scene's world array
 };
