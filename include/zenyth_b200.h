@@ -202,6 +202,11 @@ int zn_scene_expand_visible_signalled(zn_scene* scene, const void* records_dev, 
 #define ZN_EXPAND_GRID 0
 #define ZN_EXPAND_WORKLIST 1
 int zn_scene_set_expand_mode(zn_scene* scene, int mode);
+/* The leading levels of a hierarchy whose tiles fit one CTA's shared memory (at most 5 tiles of 256 entities in
+ * total, at least two levels: 7 + 56 + 448 entities in the bench scene) are composed by ONE launch that keeps their
+ * world matrices on chip (scene_top_kernel) instead of one launch per level.  Results are bit-identical; the switch
+ * exists for A/B measurement.  Default: on. */
+int zn_scene_set_level_fusion(zn_scene* scene, int enabled);
 /* Added to every index written to the visible list (shard -> global numbering). */
 int zn_scene_set_index_base(zn_scene* scene, uint32_t index_base);
 

@@ -209,6 +209,7 @@ public:
 	void SetIndexBase(uint32_t base) { detail::Check(zn_scene_set_index_base(m_scene, base), "Scene::SetIndexBase"); }
 	// Record expansion strategy (multi-GPU): a warp per group (default, dense visible sets) or classification + work
 	// list (sparse visible sets: a camera inside the scene).
+	void SetLevelFusion(bool on) { detail::Check(zn_scene_set_level_fusion(m_scene, on ? 1 : 0), "Scene::SetLevelFusion"); }
 	void SetExpandWorkList(bool on) { detail::Check(zn_scene_set_expand_mode(m_scene, on ? ZN_EXPAND_WORKLIST : ZN_EXPAND_GRID), "Scene::SetExpandWorkList"); }
 
 	// One frame, asynchronous: world matrices over the hierarchy, MVP, visible list (the fused form,

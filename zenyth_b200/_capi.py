@@ -101,6 +101,7 @@ PROTOTYPES = {
     "zn_scene_expand_visible_signalled": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, vp, vp, C.c_uint32, vp,
                                                     vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
     "zn_scene_set_expand_mode": (C.c_int, [vp, C.c_int]),
+    "zn_scene_set_level_fusion": (C.c_int, [vp, C.c_int]),
     "zn_scene_set_index_base": (C.c_int, [vp, C.c_uint32]),
     "zn_scene_update": (C.c_int, [vp]),
     "zn_scene_update_world": (C.c_int, [vp]),

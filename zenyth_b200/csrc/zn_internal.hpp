@@ -121,6 +121,8 @@ struct zn_scene {
 	uint32_t* expand_count = nullptr;      // [2] by launch parity
 	uint32_t expand_parity = 0;
 	int max_ctas_expand = 0;               // co-resident CTAs of expand_work_kernel
+	bool level_fusion = true;              // zn_scene_set_level_fusion
+	uint32_t top_levels = 0;               // leading levels composed by scene_top_kernel (0: none qualify)
 	int expand_mode = 0;                   // ZN_EXPAND_GRID / ZN_EXPAND_WORKLIST (zn_scene_set_expand_mode)
 	cudaEvent_t cull_events[3] = {nullptr, nullptr, nullptr};   // profiling: before cull, after cull, after emit
 	uint32_t* host_count = nullptr;      // pinned [1]

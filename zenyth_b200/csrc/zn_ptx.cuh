@@ -70,6 +70,9 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // Wait until the sources (smem) of all committed bulk stores have been read.
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... of all but the latest N committed groups.
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_but() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 // Wait until all committed bulk stores are complete (writes performed).
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 

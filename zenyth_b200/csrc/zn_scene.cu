@@ -30,6 +30,8 @@ static cudaError_t set_kernel_attributes() {
 	ZN_ATTR((scene_level_kernel<true, false>), kWorldSmem)
 	ZN_ATTR((scene_level_kernel<false, false>), kWorldSmem)
 	ZN_ATTR(scene_cull_kernel, kCullSmem)
+	ZN_ATTR(scene_top_kernel<true>, kTopSmemView)
+	ZN_ATTR(scene_top_kernel<false>, kTopSmemWorld)
 #undef ZN_ATTR
 	return cudaSuccess;
 }
@@ -182,6 +184,12 @@ int zn_scene_create(zn_ctx* ctx, const zn_scene_desc* desc, zn_scene** out_scene
 		int rc = encode_matrix_tensor_map(&s->tm_world_all, s->world, E);
 		if (rc == ZN_OK) rc = encode_matrix_tensor_map(&s->tm_mvp_all, s->mvp, E);
 		if (rc != ZN_OK) return cleanup(rc);
+	}
+	// the leading levels that scene_top_kernel composes in one launch: as many as fit kTopTiles tiles, at least two
+	{
+		uint32_t tiles = 0, n = 0;
+		while (n < s->levels.size() && tiles + s->levels[n].tiles <= uint32_t(kTopTiles)) tiles += s->levels[n++].tiles;
+		s->top_levels = n >= 2 ? n : 0u;
 	}
 	*out_scene = s;
 	return ZN_OK;
@@ -440,6 +448,12 @@ int zn_scene_wait_flags(zn_scene* s, const void* flags_dev, uint32_t flag_stride
 	return ZN_OK;
 }
 
+int zn_scene_set_level_fusion(zn_scene* s, int enabled) {
+	ZN_REQUIRE(s, "zn_scene_set_level_fusion: scene is NULL");
+	s->level_fusion = enabled != 0;
+	return ZN_OK;
+}
+
 int zn_scene_set_expand_mode(zn_scene* s, int mode) {
 	ZN_REQUIRE(s, "zn_scene_set_expand_mode: scene is NULL");
 	ZN_REQUIRE(mode == ZN_EXPAND_GRID || mode == ZN_EXPAND_WORKLIST, "zn_scene_set_expand_mode: unknown mode %d", mode);
@@ -552,7 +566,31 @@ static int run_update(zn_scene* s, bool with_view) {
 	cfg.dynamicSmemBytes = with_view ? kLevelSmem : kWorldSmem;
 	cfg.stream = ctx->stream;
 	cfg.attrs = &pdl;
-	for (size_t l = 0; l < s->levels.size(); ++l) {
+	size_t l_first = 0;
+	if (s->level_fusion && s->top_levels && !prof) {
+		// the top of the tree in one launch of one CTA, in place of level 0 (same dependency rules)
+		TopMaps maps;
+		TopLevels top = {};
+		top.levels = s->top_levels;
+		for (uint32_t l = 0; l < s->top_levels; ++l) {
+			const zn_level& lv = s->levels[l];
+			maps.world[l] = lv.tm_world;
+			maps.mvp[l] = lv.tm_mvp;
+			top.begin[l] = lv.begin;
+			top.end[l] = lv.end;
+			top.tiles += lv.tiles;
+		}
+		cfg.gridDim = dim3(1);
+		cfg.dynamicSmemBytes = with_view ? kTopSmemView : kTopSmemWorld;
+		cfg.numAttrs = s->inputs_touched ? 0 : 1;
+		if (with_view)
+			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_top_kernel<true>, maps, fc, top, (const uint32_t*)s->blocks, rec.ptr[0], header_words, totals, defer_wait));
+		else
+			ZN_CUDA(cudaLaunchKernelEx(&cfg, scene_top_kernel<false>, maps, fc, top, (const uint32_t*)s->blocks, rec.ptr[0], header_words, totals, defer_wait));
+		cfg.dynamicSmemBytes = with_view ? kLevelSmem : kWorldSmem;
+		l_first = s->top_levels;
+	}
+	for (size_t l = l_first; l < s->levels.size(); ++l) {
 		zn_level& lv = s->levels[l];
 		const uint32_t grid = std::min<uint32_t>(lv.tiles, uint32_t(with_view ? s->max_ctas : s->max_ctas_world));
 		cfg.gridDim = dim3(grid);
@@ -720,7 +758,9 @@ int zn_scene_level_times(zn_scene* s, float* out_ms, uint32_t capacity, float* o
 
 int zn_scene_launches_per_update(zn_scene* s, uint32_t* out_launches) {
 	ZN_REQUIRE(s && out_launches, "zn_scene_launches_per_update: NULL argument");
-	*out_launches = uint32_t(s->levels.size()) + 1;
+	// one launch per level — the fused leading levels (scene_top_kernel) count as one — plus the emit kernel
+	const uint32_t fused = (s->level_fusion && s->top_levels && !s->profiling) ? s->top_levels - 1u : 0u;
+	*out_launches = uint32_t(s->levels.size()) - fused + 1;
 	return ZN_OK;
 }
 

@@ -262,6 +262,156 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 	}
 }
 
+// scene_top_kernel — the TOP OF THE TREE in one launch of ONE CTA.  The leading levels of a hierarchy are
+// tiny (7, 56, 448 entities in the bench scene) and each costs a level kernel its whole latency chain —
+// wait for the level before, pull the parents back from L2, compute, store, complete — about 6 us per
+// level however few entities it has.  Here the leading levels whose tiles (at most kTopTiles in total)
+// fit one CTA's shared memory are composed back to back: every input block is requested up front (they
+// depend on nothing), the world tiles stay in shared memory in the swizzled layout they are stored
+// from, and a child reads its parent's matrix from there — no round trip through L2 between levels,
+// only a block barrier.  Results leave exactly as the level kernel's do (tensor stores through the
+// per-level maps, mask words, chunk total), bit for bit: same device functions, same operands.
+// Launched in place of level 0 (same programmatic dependency, same defer_wait rule), so behind an emit
+// kernel the whole top of the tree hides in that kernel's shadow.
+constexpr int kTopTiles = 5;
+constexpr uint32_t kTopSmemView = uint32_t(kTopTiles) * (kTile * 64u + kInBytes) + 2u * kTile * 64u + 1024u;   // 193 KiB
+constexpr uint32_t kTopSmemWorld = uint32_t(kTopTiles) * (kTile * 64u + kInBytes) + 1024u;                     // 161 KiB
+struct TopLevels {
+	uint32_t levels;              // fused levels, >= 2 (levels <= tiles <= kTopTiles)
+	uint32_t tiles;               // their tiles in total; tile i of the scene is tile i of the run (level 0 starts at tile 0)
+	uint32_t begin[kTopTiles];    // entity range of each fused level
+	uint32_t end[kTopTiles];
+};
+struct TopMaps {
+	CUtensorMap world[kTopTiles];   // per level, clipped at the level end
+	CUtensorMap mvp[kTopTiles];
+};
+
+template <bool WITH_VIEW>
+__global__ void __launch_bounds__(kTile, 1)
+scene_top_kernel(const __grid_constant__ TopMaps maps, const __grid_constant__ FrameConst fc, const __grid_constant__ TopLevels top,
+                 const uint32_t* __restrict__ blocks, uint32_t* __restrict__ record, uint32_t header_words,
+                 uint32_t* __restrict__ chunk_total, uint32_t defer_wait) {
+	extern __shared__ uint8_t smem_raw[];
+	__shared__ uint64_t s_full[kTopTiles];
+	__shared__ uint32_t s_mask[2][kWarpsPerTile];
+
+	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	float4* world_tiles = reinterpret_cast<float4*>(smem);                                        // [kTopTiles][kTile * 4], swizzled
+	float4* mvp_tiles = reinterpret_cast<float4*>(smem + kTopTiles * kTile * 64);                 // [2][kTile * 4], WITH_VIEW only
+	const uint32_t* in_blocks = reinterpret_cast<const uint32_t*>(smem + kTopTiles * kTile * 64 + (WITH_VIEW ? 2 * kTile * 64 : 0));
+
+	const int t = threadIdx.x;
+	const int lane = t & 31;
+	const int warp = t >> 5;
+
+	if (t == 0) {
+		for (uint32_t i = 0; i < top.tiles; ++i) mbar_init(&s_full[i], 1);
+		fence_mbar_init();
+		for (uint32_t l = 0; l < top.levels; ++l) {
+			prefetch_tensormap(&maps.world[l]);
+			if (WITH_VIEW) prefetch_tensormap(&maps.mvp[l]);
+		}
+		grid_dep_launch();
+		// the input blocks depend on nothing before this kernel on the stream (an upload makes this a normal launch)
+		for (uint32_t i = 0; i < top.tiles; ++i) {
+			uint32_t* dst = const_cast<uint32_t*>(in_blocks) + size_t(i) * kBlockWords;
+			const uint32_t* src = blocks + size_t(i) * kBlockWords;
+			if (WITH_VIEW) {
+				mbar_arrive_expect_tx(&s_full[i], kInBytes);
+				bulk_g2s(dst, src, kInBytes, &s_full[i]);
+			} else {
+				mbar_arrive_expect_tx(&s_full[i], 10u * kTile * 4u);
+				bulk_g2s(dst, src, 9u * kTile * 4u, &s_full[i]);
+				bulk_g2s(dst + 15 * kTile, src + 15 * kTile, kTile * 4u, &s_full[i]);
+			}
+		}
+		// everything this kernel WRITES is ordered behind the kernel before it — see scene_level_kernel for defer_wait
+		if (!defer_wait) grid_dep_wait();
+	}
+	__syncthreads();
+
+	uint32_t i = 0;          // tile of the run == global tile
+	uint32_t total = 0;      // visible entities of the run (warp 0, lane 0); all its tiles belong to chunk 0
+	for (uint32_t l = 0; l < top.levels; ++l) {
+		const uint32_t begin = top.begin[l], end = top.end[l];
+		for (uint32_t first = begin; first < end; first += kTile, ++i) {
+			mbar_wait(&s_full[i], 0);
+			const uint32_t* in_blk = in_blocks + size_t(i) * kBlockWords;
+			float v[15];
+#pragma unroll
+			for (int k = 0; k < (WITH_VIEW ? 15 : 9); ++k) v[k] = __uint_as_float(in_blk[k * kTile + t]);
+			const bool live = first + t < end;
+			const uint32_t p = (l > 0 && live) ? in_blk[15 * kTile + t] : ZN_NO_PARENT;
+			Affine P;
+			if (p != ZN_NO_PARENT) {
+				// the parent lives in an earlier level (upload contract), i.e. in one of the tiles already composed
+				uint32_t pl = l - 1;
+				while (p < top.begin[pl]) --pl;
+				uint32_t pt = 0;
+				for (uint32_t q = 0; q < pl; ++q) pt += (top.end[q] - top.begin[q] + kTile - 1) / kTile;
+				const uint32_t row = p - top.begin[pl];
+				const float4* src = world_tiles + (size_t(pt) + (row >> 8)) * (kTile * 4) + (row & 255u) * 4;
+				const int sw = ((row & 255u) >> 1) & 3;
+				const float4 c0 = src[0 ^ sw], c1 = src[1 ^ sw], c2 = src[2 ^ sw], c3 = src[3 ^ sw];
+				P.m[0][0] = c0.x; P.m[1][0] = c0.y; P.m[2][0] = c0.z;
+				P.m[0][1] = c1.x; P.m[1][1] = c1.y; P.m[2][1] = c1.z;
+				P.m[0][2] = c2.x; P.m[1][2] = c2.y; P.m[2][2] = c2.z;
+				P.m[0][3] = c3.x; P.m[1][3] = c3.y; P.m[2][3] = c3.z;
+			}
+			if (WITH_VIEW) {
+				// the MVP tile is double-buffered: the stores of tile i-2 must have finished reading this one
+				if (t == 0) bulk_wait_read_but<1>();
+				__syncthreads();
+			}
+			const Affine local = local_trs(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+			Affine w = local;
+			if (p != ZN_NO_PARENT) w = affine_mul(P, local);
+			if (WITH_VIEW) {
+				const bool vis = live && aabb_visible(w, v[9], v[10], v[11], v[12], v[13], v[14], fc.planes);
+				const uint32_t mask = __ballot_sync(0xffffffffu, vis);
+				if (lane == 0) s_mask[i & 1u][warp] = mask;
+			}
+			float4* out_world = world_tiles + size_t(i) * (kTile * 4);
+			float4* out_mvp = mvp_tiles + size_t(i & 1u) * (kTile * 4);
+			{
+				const int sw = (t >> 1) & 3;
+				float4* wr = out_world + t * 4;
+				wr[0 ^ sw] = make_float4(w.m[0][0], w.m[1][0], w.m[2][0], 0.0f);
+				wr[1 ^ sw] = make_float4(w.m[0][1], w.m[1][1], w.m[2][1], 0.0f);
+				wr[2 ^ sw] = make_float4(w.m[0][2], w.m[1][2], w.m[2][2], 0.0f);
+				wr[3 ^ sw] = make_float4(w.m[0][3], w.m[1][3], w.m[2][3], 1.0f);
+				if (WITH_VIEW) {
+					float m[16];
+					mvp_mul(fc.vp, w, m);
+					float4* mr = out_mvp + t * 4;
+					mr[0 ^ sw] = make_float4(m[0], m[1], m[2], m[3]);
+					mr[1 ^ sw] = make_float4(m[4], m[5], m[6], m[7]);
+					mr[2 ^ sw] = make_float4(m[8], m[9], m[10], m[11]);
+					mr[3 ^ sw] = make_float4(m[12], m[13], m[14], m[15]);
+				}
+			}
+			fence_proxy_async_smem();
+			__syncthreads();             // the tile is complete: its children may read it, the TMA unit may store it
+			if (t == 0) {
+				tensor_store_2d(&maps.world[l], out_world, 0, int32_t(first));
+				if (WITH_VIEW) tensor_store_2d(&maps.mvp[l], out_mvp, 0, int32_t(first));
+				bulk_commit();
+			}
+			if (WITH_VIEW && warp == 0) {
+				const uint32_t word = (lane < kWarpsPerTile) ? s_mask[i & 1u][lane] : 0u;
+				if (lane < kWarpsPerTile) record[header_words + size_t(i) * kWarpsPerTile + lane] = word;
+				total += __reduce_add_sync(0xffffffffu, __popc(word));
+			}
+		}
+	}
+	if (WITH_VIEW && t == 0 && total) atomicAdd(chunk_total, total);
+	if (t == 0) {
+		bulk_wait_read_all();
+		if (defer_wait) grid_dep_wait();
+	}
+}
+
 // scene_cull_kernel — a camera pass over world matrices that already exist (zn_scene_cull): what
 // Scene::Cull(camera) runs from OnRender (Core/src/Application.cpp:49-51) after OnUpdate (:47) has
 // composed the hierarchy, and again for every further view (shadow pass, second camera) without

@@ -314,6 +314,11 @@ class Scene:
         or classification + work list (sparse visible sets).  zn_scene_set_expand_mode."""
         check(self._lib.zn_scene_set_expand_mode(self._h, 1 if worklist else 0))
 
+    def SetLevelFusion(self, on: bool) -> None:
+        """The tiny leading levels of a hierarchy in one launch that keeps their matrices on chip (default on; results
+        are bit-identical either way).  zn_scene_set_level_fusion."""
+        check(self._lib.zn_scene_set_level_fusion(self._h, 1 if on else 0))
+
     def SetIndexBase(self, base: int) -> None:
         check(self._lib.zn_scene_set_index_base(self._h, base))
 
