@@ -20,7 +20,7 @@ offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
 sc = zn.Scene(ctx, E, offs)
 sc.FillSynthetic(0x5A454E59 + 3, 8, 0.0)
 out = {}
-for eye_z in (1500.0, 0.0):
+for eye_z in (1500.0, 600.0, 0.0):
     sc.SetCamera(zn.Camera(zn.CameraDesc(eye=(0.0, 0.0, eye_z), center=(0.0, 0.0, eye_z - 1.0))))
     words = sc.DeviceBuffers().visibility_record_words
     R = 7
@@ -35,18 +35,21 @@ for eye_z in (1500.0, 0.0):
     counts = torch.zeros(R, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     res = {"visible": n_vis, "fraction": n_vis / E}
-    for r in (1, 3, 7):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(3):
-            sc.ExpandVisible(recs.data_ptr(), r, words, lists.data_ptr(), E, counts.data_ptr())
-        a.record(stream)
-        for _ in range(20):
-            sc.ExpandVisible(recs.data_ptr(), r, words, lists.data_ptr(), E, counts.data_ptr())
-        b.record(stream)
-        torch.cuda.synchronize()
-        us = a.elapsed_time(b) / 20 * 1e3
-        res[f"expand_{r}_us"] = us
-        res[f"expand_{r}_write_GBs"] = r * n_vis * 4 / (us * 1e-6) / 1e9
+    for mode, worklist in (("", False), ("worklist_", True)):
+        sc.SetExpandMode(worklist)
+        for r in (1, 3, 7):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                sc.ExpandVisible(recs.data_ptr(), r, words, lists.data_ptr(), E, counts.data_ptr())
+            a.record(stream)
+            for _ in range(20):
+                sc.ExpandVisible(recs.data_ptr(), r, words, lists.data_ptr(), E, counts.data_ptr())
+            b.record(stream)
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) / 20 * 1e3
+            res[f"{mode}expand_{r}_us"] = us
+            res[f"{mode}expand_{r}_write_GBs"] = r * n_vis * 4 / (us * 1e-6) / 1e9
+    sc.SetExpandMode(False)
     # a plain device memset of the same bytes: what a pure write stream reaches here
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     view = lists[: 7 * n_vis]
