@@ -73,7 +73,7 @@ def test_partial_uploads_across_level_boundaries(oracle, gpu_ctx):
     sc.SetCamera(zn.Camera(view=view, proj=proj))
     sc.Update()
     rng = np.random.default_rng(5)
-    for first, count in [(290, 20), (0, 1), (999, 2), (2499, 1), (250, 1800)]:   # ranges straddling level edges
+    for first, count in [(290, 20), (0, 1), (999, 2), (2499, 1), (250, 1800), (292, 16), (990, 17)]:   # ranges straddling level edges; <= 16 entities travel as kernel parameters
         arrays["position"][first:first + count] += rng.uniform(-5, 5, (count, 3)).astype(np.float32)
         arrays["rotation"][first:first + count] = rng.uniform(-3, 3, (count, 3)).astype(np.float32)
         sc.SetTransforms(arrays["position"][first:first + count], arrays["rotation"][first:first + count], None, first=first)
@@ -84,6 +84,34 @@ def test_partial_uploads_across_level_boundaries(oracle, gpu_ctx):
         assert same_values(sc.World(), ref["world"]) and np.array_equal(sc.Visible(), ref["visible"]), (first, count)
     back = sc.Inputs()
     assert np.array_equal(back["position"], arrays["position"]) and np.array_equal(back["parent"], arrays["parent"])
+    sc.Close()
+
+
+def test_handful_of_entities_with_padded_records_and_single_arrays(oracle, gpu_ctx):
+    """<= 16 entities take the one-launch path (values as kernel parameters): 16-byte records (the reference's vec3),
+    one array at a time, across a level edge."""
+    import zenyth_b200 as zn
+    arrays = oracle.synth_scene(BASE_SEED + 12, [300, 700, 1500], fanout=3, center_range=0.2)
+    view, proj = camera(oracle)
+    sc = zn.Scene(gpu_ctx, 2500, arrays["level_offsets"])
+    sc.Load(arrays)
+    sc.SetCamera(zn.Camera(view=view, proj=proj))
+    rng = np.random.default_rng(8)
+
+    def pad(a):
+        out = np.full((a.shape[0], 4), np.float32(7.0), np.float32)     # the w lane is never read
+        out[:, :3] = a
+        return out
+    for key, first, count in [("scale", 296, 9), ("rotation", 0, 16), ("position", 995, 12), ("scale", 2499, 1)]:
+        lo, hi = {"scale": (0.5, 2.0), "rotation": (-3.0, 3.0), "position": (-50.0, 50.0)}[key]
+        arrays[key][first:first + count] = rng.uniform(lo, hi, (count, 3)).astype(np.float32)
+        sc.SetTransforms(**{key: pad(arrays[key][first:first + count])}, first=first, count=count)
+        sc.Update()
+        ref = oracle.scene_update(arrays, view, proj)
+        assert same_values(sc.World(), ref["world"]) and np.array_equal(sc.Visible(), ref["visible"]), (key, first, count)
+    back = sc.Inputs()
+    for key in ("position", "rotation", "scale"):
+        assert np.array_equal(back[key], arrays[key]), key
     sc.Close()
 
 

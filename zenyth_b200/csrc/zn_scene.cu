@@ -227,6 +227,27 @@ int zn_scene_set_transforms(zn_scene* s, uint32_t first, uint32_t count, const f
 	if (rc == ZN_OK) rc = check_stride(stride_bytes, "zn_scene_set_transforms");
 	if (rc != ZN_OK) return rc;
 	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	if (count <= kPatchEntities && s->tile_count <= 0xFFFFFFFFu / kBlockWords) {
+		// a handful of moved entities: one launch carrying the values as parameters (no staging copy, no repack passes)
+		if (count == 0 || (!position && !rotation && !scale)) return ZN_OK;
+		PatchRows patch = {};
+		patch.count = count;
+		patch.rows = (position ? 0x007u : 0u) | (rotation ? 0x038u : 0u) | (scale ? 0x1C0u : 0u);
+		size_t l = 0;
+		for (uint32_t k = 0; k < count; ++k) {
+			const uint32_t i = first + k;
+			while (i >= s->levels[l].end) ++l;
+			const uint32_t rel = i - s->levels[l].begin;
+			patch.at[k] = (s->levels[l].tile_base + rel / kTile) * kBlockWords + rel % kTile;
+			const float* src[3] = {position, rotation, scale};
+			for (int a = 0; a < 3; ++a)
+				if (src[a]) std::memcpy(&patch.v[k][a * 3], reinterpret_cast<const uint8_t*>(src[a]) + size_t(k) * stride_bytes, 12);
+		}
+		s->inputs_touched = true;
+		patch_rows_kernel<<<1, kPatchEntities * 9, 0, s->ctx->stream>>>(s->blocks, patch);
+		ZN_CUDA(cudaGetLastError());
+		return ZN_OK;
+	}
 	if ((rc = upload3(s, 0, first, count, position, stride_bytes)) != ZN_OK) return rc;
 	if ((rc = upload3(s, 3, first, count, rotation, stride_bytes)) != ZN_OK) return rc;
 	return upload3(s, 6, first, count, scale, stride_bytes);

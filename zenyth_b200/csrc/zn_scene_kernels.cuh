@@ -1091,6 +1091,19 @@ __global__ void repack3_kernel(const uint32_t* __restrict__ src, uint32_t stride
 	const uint32_t* s = src + size_t(j) * stride_w;
 	d[0] = s[0]; d[kTile] = s[1]; d[2 * kTile] = s[2];
 }
+// A HANDFUL of entities (the few that a frame's game logic moved): the values travel in the kernel's
+// parameters — no staging copy, one launch for position, rotation and scale together.
+constexpr uint32_t kPatchEntities = 16;
+struct PatchRows {
+	uint32_t at[kPatchEntities];          // word offset of the entity's lane in row 0 of its block
+	float v[kPatchEntities][9];           // rows 0..8: position, rotation, scale
+	uint32_t count;
+	uint32_t rows;                        // bit r: row r is present
+};
+__global__ void patch_rows_kernel(uint32_t* __restrict__ blocks, const __grid_constant__ PatchRows patch) {
+	const uint32_t e = threadIdx.x / 9u, r = threadIdx.x % 9u;
+	if (e < patch.count && ((patch.rows >> r) & 1u)) blocks[size_t(patch.at[e]) + r * kTile] = __float_as_uint(patch.v[e][r]);
+}
 // One launch for a whole host frame (zn_scene_frame_host_submit): up to three packed [count][3]
 // arrays (position / rotation / scale, NULL = absent) of entities [first, first+count) into rows
 // 0..8 of the tile-major blocks, across every level the range touches.
