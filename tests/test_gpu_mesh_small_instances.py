@@ -56,3 +56,28 @@ def test_mixed_large_and_small(oracle, gpu_ctx):
 def test_vertex_count_not_a_multiple_of_four(oracle, gpu_ctx):
     for tail in (1, 2, 3):
         run(oracle, gpu_ctx, [1024, 512 + tail])
+
+
+@pytest.mark.parametrize("instances,verts", [(20000, 1), (9000, 2), (7001, 3), (5000, 4), (3000, 8), (5000, 36), (300, 100),
+                                             (33, 1000), (9, 1025), (5, 3000), (1024, 1), (1025, 1)])
+def test_equal_ranges_without_a_table_equal_the_explicit_table_and_the_oracle(oracle, gpu_ctx, instances, verts):
+    """A mesh created WITHOUT instance_first_vertex has equal ranges: its kernel derives every boundary arithmetically
+    (no table read).  Same results as the same ranges passed explicitly, and as the oracle."""
+    import zenyth_b200 as zn
+    V = instances * verts
+    first = (np.arange(instances + 1, dtype=np.uint64) * verts).astype(np.uint32)
+    pos, nrm = oracle.synth_mesh(BASE_SEED + 5, V)
+    models = models_for(oracle, instances)
+    ref_p, ref_n = oracle.mesh_transform(first, models, pos, nrm, threads=oracle.hardware_threads())
+    got = []
+    for table in (None, first):
+        mesh = zn.Mesh(gpu_ctx, V, instances, table)
+        mesh.SetVertices(pos, nrm)
+        mesh.SetModels(models)
+        mesh.Transform()
+        got.append(mesh.Read())
+        mesh.Close()
+    for p, n in got:
+        assert same_values(p, ref_p) and same_values(n, ref_n)
+    assert np.array_equal(got[0][0].view(np.uint32), got[1][0].view(np.uint32))
+    assert np.array_equal(got[0][1].view(np.uint32), got[1][1].view(np.uint32))
