@@ -27,8 +27,13 @@ for verts, inst, table in ((1024, 65536, False), (36, 1 << 20, False), (8, 1 << 
     scene = zn.Scene(ctx, inst)
     scene.FillSynthetic(0x5A454E59 + 2, 1, 0.0)
     scene.UpdateWorld()
-    # table=True: the same equal ranges given as an explicit instance_first_vertex array (what a ragged batch runs)
-    mesh = zn.Mesh(ctx, V, inst, (np.arange(inst + 1, dtype=np.uint64) * verts).astype(np.uint32) if table else None)
+    # table=True: a ragged batch of the same mean size — every other boundary moved by one vertex — so that the kernel
+    # really reads instance_first_vertex (an explicit table of EQUAL ranges is recognised and runs the arithmetic path)
+    first = None
+    if table:
+        first = (np.arange(inst + 1, dtype=np.uint64) * verts).astype(np.uint32)
+        first[1:-1:2] += 1
+    mesh = zn.Mesh(ctx, V, inst, first)
     mesh.FillSynthetic(0x5A454E59 + 4)
     mesh.BindSceneModels(scene, 0)
     for _ in range(3):

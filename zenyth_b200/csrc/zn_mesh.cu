@@ -357,7 +357,10 @@ int zn_mesh_create(zn_ctx* ctx, const zn_mesh_desc* desc, zn_mesh** out_mesh) {
 	ZN_TRY(cudaMemcpyAsync(m->instance_first_vertex, first.data(), (size_t(I) + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
 	m->multi_instance_tiles = multi;
 	m->needs_inst_mats = table;
-	m->uniform_vpi = (!desc->instance_first_vertex && !table) ? V / I : 0u;   // equal ranges: boundaries are arithmetic
+	// equal ranges — no table given, or a table that says so: boundaries are arithmetic, the kernel never reads the table
+	bool equal_ranges = V % I == 0;
+	for (uint32_t k = 0; equal_ranges && k <= I; ++k) equal_ranges = first[k] == uint32_t(uint64_t(V / I) * k);
+	m->uniform_vpi = (equal_ranges && !table) ? V / I : 0u;
 	m->smem_window = window;
 	if (table) ZN_TRY(cudaMalloc(&m->inst_mats, size_t(I) * kInstMatFloats * 4));
 	ZN_TRY(cudaMalloc(&m->models_own, size_t(I) * 64));
