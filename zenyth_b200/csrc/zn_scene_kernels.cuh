@@ -47,7 +47,8 @@ constexpr uint32_t kParSlots = 64;                         // parent matrices st
 constexpr uint32_t kParBytes = kParSlots * 64;             // 4 KiB
 constexpr uint32_t kOutBytes = 2 * kTile * 64;             // world tile + mvp tile
 constexpr uint32_t kLevelSmem = kOutBytes + kInBytes + kParBytes + 1024;
-constexpr uint32_t kWorldSmem = kTile * 64 + kInBytes + kParBytes + 1024;   // WITH_VIEW = false: no MVP tile, 37 KiB, five CTAs per SM
+constexpr uint32_t kWorldInBytes = 10u * kTile * 4u;       // WITH_VIEW = false stages rows 0..8 and the parent row only (10 KiB)
+constexpr uint32_t kWorldSmem = kTile * 64 + kWorldInBytes + kParBytes + 1024;   // no MVP tile: 31 KiB, six CTAs per SM
 constexpr uint32_t kGather = 0xFFFFFFFFu;                  // tile_prange.y: parents too scattered to stage
 constexpr int kChunkTiles = 32;                            // tiles per emit CTA (8192 entities)
 constexpr uint32_t kSmallLevelTiles = 4096;                // levels below 1Mi entities leave their peer stores to the emit kernel
@@ -97,7 +98,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // rows 0..8 and the parent row of a block (10 KiB instead of 16), stores the world tile and writes
 // neither MVPs nor masks; a later scene_cull_kernel pass supplies those per camera.
 template <bool HAS_PARENT, bool WITH_VIEW>
-__global__ void __launch_bounds__(kTile, WITH_VIEW ? 4 : 5)
+__global__ void __launch_bounds__(kTile, WITH_VIEW ? 4 : 6)
 scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_constant__ CUtensorMap tm_mvp,
                    const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
                    const uint2* __restrict__ tile_prange, const float* __restrict__ world_rd,
@@ -116,7 +117,8 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 	float4* out_world = reinterpret_cast<float4*>(smem);
 	float4* out_mvp = reinterpret_cast<float4*>(smem + kTile * 64);   // WITH_VIEW only
 	const uint32_t* in_blk = reinterpret_cast<const uint32_t*>(smem + out_bytes);
-	const float4* in_par = reinterpret_cast<const float4*>(smem + out_bytes + kInBytes);
+	const float4* in_par = reinterpret_cast<const float4*>(smem + out_bytes + (WITH_VIEW ? kInBytes : kWorldInBytes));
+	constexpr int kParentRow = WITH_VIEW ? 15 : 9;   // where the block's parent row is staged
 
 	const int t = threadIdx.x;
 	const int lane = t & 31;
@@ -139,7 +141,7 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		} else {
 			mbar_arrive_expect_tx(&s_full, 10u * kTile * 4u + (staged ? pr.y * 64u : 0u));
 			bulk_g2s(const_cast<uint32_t*>(in_blk), blocks + size_t(gt) * kBlockWords, 9u * kTile * 4u, &s_full);
-			bulk_g2s(const_cast<uint32_t*>(in_blk) + 15 * kTile, blocks + size_t(gt) * kBlockWords + 15 * kTile, kTile * 4u, &s_full);
+			bulk_g2s(const_cast<uint32_t*>(in_blk) + kParentRow * kTile, blocks + size_t(gt) * kBlockWords + 15 * kTile, kTile * 4u, &s_full);
 		}
 		// everything from here on is ordered behind the kernel before this one on the stream — unless this launch touches
 		// nothing that kernel reads or writes (defer_wait: level 0 of a frame running beside the previous frame's emit)
@@ -170,7 +172,7 @@ scene_level_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_co
 		float v[15];
 #pragma unroll
 		for (int k = 0; k < (WITH_VIEW ? 15 : 9); ++k) v[k] = __uint_as_float(in_blk[k * kTile + t]);
-		const uint32_t p = HAS_PARENT ? in_blk[15 * kTile + t] : ZN_NO_PARENT;
+		const uint32_t p = HAS_PARENT ? in_blk[kParentRow * kTile + t] : ZN_NO_PARENT;
 		Affine P;
 		if (HAS_PARENT && p != ZN_NO_PARENT) {
 			const uint2 pr = s_meta;
