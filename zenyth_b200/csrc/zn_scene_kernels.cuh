@@ -611,6 +611,11 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 	const uint32_t tile = chunk * kChunkTiles + (t >> 3);
 	const uint32_t word = (tile < tiles) ? __ldcg(masks + size_t(tile) * kWarpsPerTile + (t & 7)) : 0u;
 	const uint32_t ctot = __ldcg(totals + chunk);
+	// first entity of this warp's 4-tile group: only a full chunk uses it, but fetching it here keeps a dependent
+	// load off the path between the block barriers and the stores
+	const uint32_t group_tile = chunk * kChunkTiles + uint32_t(warp) * 4u;
+	const uint32_t group_first = (group_tile < tiles) ? __ldg(tile_first_entity + group_tile) : 0u;
+	const uint32_t tile_first = ((t & 7) == 0 && tile < tiles) ? __ldg(tile_first_entity + tile) + index_base : 0u;   // mixed chunks
 	uint32_t acc = 0;
 	for (uint32_t j = t; j < chunk; j += 256) acc += __ldcg(totals + j);
 	acc = __reduce_add_sync(0xffffffffu, acc);
@@ -640,7 +645,7 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 		}
 		if (ctot == 0u) return 0u;
 		__syncthreads();
-		store_run_1024(visible + s_base + uint32_t(warp) * 4u * kTile, tile_first_entity[chunk * kChunkTiles + warp * 4] + index_base, lane);
+		store_run_1024(visible + s_base + uint32_t(warp) * 4u * kTile, group_first + index_base, lane);
 		return ctot;
 	}
 
@@ -693,7 +698,7 @@ __device__ __forceinline__ uint32_t emit_chunk(const uint32_t* __restrict__ tota
 	__shared__ uint32_t s_first[kChunkTiles];
 	s_word[t] = word;
 	s_off[t] = my_off;
-	if ((t & 7) == 0) s_first[t >> 3] = (tile < tiles) ? tile_first_entity[tile] + index_base : 0u;
+	if ((t & 7) == 0) s_first[t >> 3] = tile_first;
 	__syncwarp();
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint4* w4 = reinterpret_cast<const uint4*>(s_word + warp * 32);
