@@ -46,6 +46,7 @@
 #include "zn_internal.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -334,6 +335,16 @@ int zn_exchange_bind(zn_exchange* x, zn_scene* const* scenes, uint32_t scene_cou
 	return ZN_OK;
 }
 
+// Measurement knob (A/B runs on one box): ZN_EXCHANGE_EARLY_START=0 launches the expansion as a normal, fully
+// stream-ordered kernel instead of programmatically beside the tail of the update before it.
+static bool early_start_enabled() {
+	static const bool on = [] {
+		const char* v = std::getenv("ZN_EXCHANGE_EARLY_START");
+		return !(v && v[0] == '0');
+	}();
+	return on;
+}
+
 static int exchange_launch(zn_exchange* x, zn_scene* scene, int64_t frame, const uint32_t* index_bases, bool signal_only) {
 	ZN_CUDA(cudaSetDevice(x->ctx->device));
 	cudaStream_t stream = x->ctx->stream;
@@ -349,7 +360,7 @@ static int exchange_launch(zn_exchange* x, zn_scene* scene, int64_t frame, const
 	return expand_visible_on(stream, scene, signal_only ? "zn_exchange_signal" : "zn_exchange_expand", records, x->total, x->record_words,
 	                         signal_only ? 0 : int(first_own), signal_only ? x->total : x->per_rank, index_bases, x->lists + half * x->capacity,
 	                         x->capacity, x->counts + half, x->base + x->flags_offset, kFlagStrideWords, x->per_rank, uint32_t(frame + 1),
-	                         x->timeout_ms, x->status, nullptr);
+	                         x->timeout_ms, x->status, nullptr, /*early_start=*/!x->overlap && early_start_enabled());
 }
 
 int zn_exchange_signal(zn_exchange* x, zn_scene* scene) {

@@ -45,7 +45,7 @@ namespace zn {
 int expand_visible_on(cudaStream_t stream, zn_scene* s, const char* who, const void* records_dev, uint32_t record_count,
                       uint32_t record_stride_words, int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev,
                       uint32_t list_stride, void* counts_dev, const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag,
-                      uint32_t expected, uint32_t timeout_ms, void* status_dev, const void* abort_status);
+                      uint32_t expected, uint32_t timeout_ms, void* status_dev, const void* abort_status, bool early_start = false);
 } // namespace zn
 
 struct zn_ctx {

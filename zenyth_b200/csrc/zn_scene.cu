@@ -364,7 +364,7 @@ int zn_scene_set_signal_value(zn_scene* s, uint32_t value) {
 int zn::expand_visible_on(cudaStream_t stream, zn_scene* s, const char* who, const void* records_dev, uint32_t record_count,
                           uint32_t record_stride_words, int skip_index, uint32_t skip_count, const uint32_t* index_bases, void* lists_dev,
                           uint32_t list_stride, void* counts_dev, const void* flags_dev, uint32_t flag_stride_words, uint32_t records_per_flag,
-                          uint32_t expected, uint32_t timeout_ms, void* status_dev, const void* abort_status) {
+                          uint32_t expected, uint32_t timeout_ms, void* status_dev, const void* abort_status, bool early_start) {
 	ZN_REQUIRE(s && records_dev && lists_dev && counts_dev, "%s: NULL argument", who);
 	ZN_REQUIRE(record_count >= 1 && record_count <= 64, "%s: record_count %u must be in [1, 64]", who, record_count);
 	ZN_REQUIRE(record_stride_words >= s->record_words, "%s: record stride %u < record size %u words", who, record_stride_words, s->record_words);
@@ -380,6 +380,15 @@ int zn::expand_visible_on(cudaStream_t stream, zn_scene* s, const char* who, con
 		sig.value = s->signal_value;
 	}
 	if (record_count == skip_count && !flags_dev) return ZN_OK;     // nothing to expand and nothing to signal
+	// early_start (zn_exchange_expand on the context stream): the expansion of frame k-1 shares nothing with the update of
+	// frame k before it on the stream — other record slot, other half of the lists — and reads a record only behind its
+	// owner's flag, so it is launched programmatically: its CTAs start beside the tail of the emit kernel instead of behind a
+	// drained GPU.  Only the ONE thread that raises this rank's flags waits for that update to complete (griddepcontrol.wait,
+	// which also keeps the chain of completions intact for the kernels after the expansion).
+	cudaLaunchAttribute early;
+	early.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	early.val.programmaticStreamSerializationAllowed = 1;
+	const unsigned early_attrs = (early_start && flags_dev && !abort_status) ? 1u : 0u;
 	if (s->expand_mode == ZN_EXPAND_WORKLIST) {
 		// Two launches: classify every (record, group) into a work list of the non-empty ones, then a persistent grid works it off.
 		const uint32_t live = record_count - skip_count;
@@ -402,10 +411,17 @@ int zn::expand_visible_on(cudaStream_t stream, zn_scene* s, const char* who, con
 		ExpandWork work = {s->expand_entries, s->expand_count, s->expand_parity};
 		s->expand_parity ^= 1u;
 		const dim3 cgrid((groups + kClassifyThreads - 1) / kClassifyThreads, std::max<uint32_t>(1u, live));
-		expand_classify_kernel<<<cgrid, kClassifyThreads, 0, stream>>>(
-			static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count,
-			skip_index, int(skip_count), static_cast<uint32_t*>(counts_dev), static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag,
-			uint64_t(timeout_ms) * 1000000ull, static_cast<uint32_t*>(status_dev), static_cast<const uint32_t*>(abort_status), sig, work);
+		cudaLaunchConfig_t ccfg = {};
+		ccfg.gridDim = cgrid;
+		ccfg.blockDim = dim3(kClassifyThreads);
+		ccfg.stream = stream;
+		ccfg.attrs = &early;
+		ccfg.numAttrs = early_attrs;
+		ZN_CUDA(cudaLaunchKernelEx(&ccfg, expand_classify_kernel, static_cast<const uint32_t*>(records_dev), record_stride_words,
+		                           (const uint32_t*)s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count, skip_index, int(skip_count),
+		                           static_cast<uint32_t*>(counts_dev), static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected,
+		                           records_per_flag, uint64_t(timeout_ms) * 1000000ull, static_cast<uint32_t*>(status_dev),
+		                           static_cast<const uint32_t*>(abort_status), sig, work));
 		ZN_CUDA(cudaGetLastError());
 		cudaLaunchAttribute pdl;
 		pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -423,11 +439,17 @@ int zn::expand_visible_on(cudaStream_t stream, zn_scene* s, const char* who, con
 	}
 	// One CTA per (record, chunk), one warp per 4-tile group.
 	const dim3 grid((s->chunk_count + kExpandChunks - 1) / kExpandChunks, std::max<uint32_t>(1u, record_count - skip_count));
-	expand_visible_kernel<<<grid, kExpandWarps * 32, 0, stream>>>(
-		static_cast<const uint32_t*>(records_dev), record_stride_words, s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count,
-		skip_index, int(skip_count), static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),
-		static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag, uint64_t(timeout_ms) * 1000000ull,
-		static_cast<uint32_t*>(status_dev), static_cast<const uint32_t*>(abort_status), sig);
+	cudaLaunchConfig_t gcfg = {};
+	gcfg.gridDim = grid;
+	gcfg.blockDim = dim3(kExpandWarps * 32);
+	gcfg.stream = stream;
+	gcfg.attrs = &early;
+	gcfg.numAttrs = early_attrs;
+	ZN_CUDA(cudaLaunchKernelEx(&gcfg, expand_visible_kernel, static_cast<const uint32_t*>(records_dev), record_stride_words,
+	                           (const uint32_t*)s->tile_first_entity, s->tile_count, s->chunk_count, bases, record_count, skip_index, int(skip_count),
+	                           static_cast<uint32_t*>(lists_dev), list_stride, static_cast<uint32_t*>(counts_dev),
+	                           static_cast<const uint32_t*>(flags_dev), flag_stride_words, expected, records_per_flag,
+	                           uint64_t(timeout_ms) * 1000000ull, static_cast<uint32_t*>(status_dev), static_cast<const uint32_t*>(abort_status), sig));
 	ZN_CUDA(cudaGetLastError());
 	return ZN_OK;
 }
@@ -573,7 +595,12 @@ static int run_update(zn_scene* s, bool with_view) {
 	// frame).  Not after an upload: then even the input blocks are still being written.
 	// And only behind an EMIT kernel of this scene — by then every level kernel of the previous frame has completed (a
 	// world-only update ends with a level kernel that may still be reading the parents level 0 is about to rewrite).
-	const uint32_t defer_wait = (s->tail_is_emit && !s->inputs_touched && !s->profiling && (!with_view || s->frame_record != s->prev_frame_record)) ? 1u : 0u;
+	// And never a launch that stores into PEER records (a level 0 too large to leave its masks to the emit kernel): when a
+	// slot of a peer's buffer may be rewritten is settled by the expansion before this update on the stream (zn_exchange.cpp,
+	// "Slot reuse"), so such a launch waits for it like every later level does.  (scene_top_kernel never writes to peers.)
+	const bool first_launch_pushes = with_view && n_targets > 1 && small_levels == 0;
+	const uint32_t defer_wait = (s->tail_is_emit && !s->inputs_touched && !s->profiling && !first_launch_pushes &&
+	                             (!with_view || s->frame_record != s->prev_frame_record)) ? 1u : 0u;
 	// Every kernel of a frame is launched with programmatic stream serialization: its prologue (and
 	// the first input-block load) overlaps the tail of the kernel before it; it calls
 	// griddepcontrol.wait before touching anything that kernel wrote.  That includes level 0, whose
@@ -699,7 +726,10 @@ int zn_scene_cull(zn_scene* s, const float view[16], const float proj[16], const
 	zn_frustum_planes(vp, fc.planes);
 	next_frame_buffers(s);
 	// behind an emit kernel of this scene (a previous pass, or a fused update) the pass need not wait: see scene_cull_kernel
-	const uint32_t defer_wait = (s->tail_is_emit && !s->inputs_touched && !s->profiling && s->frame_record != s->prev_frame_record) ? 1u : 0u;
+	// (not with peer records bound: the pass stores masks into the peers' slots, which must stay behind the expansion that
+	// precedes it on the stream — zn_exchange.cpp, "Slot reuse")
+	const uint32_t defer_wait = (s->tail_is_emit && !s->inputs_touched && !s->profiling && s->peer_records.empty() &&
+	                             s->frame_record != s->prev_frame_record) ? 1u : 0u;
 	s->tail_is_emit = false;
 	const RecordTargets rec = record_targets(s);
 	uint32_t* totals = s->chunk_total + size_t(s->frame_parity) * s->chunk_count;

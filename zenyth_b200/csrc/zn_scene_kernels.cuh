@@ -803,7 +803,9 @@ expand_visible_kernel(const uint32_t* __restrict__ records, uint32_t record_stri
 	__shared__ uint32_t s_first[kExpandWarps][4];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	if (sig.n > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank
+		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank.  (Launched
+		// programmatically — zn_exchange_expand — this is the one thread that waits for that update; a no-op otherwise.)
+		grid_dep_wait();
 		raise_flags(sig);
 	}
 	uint32_t r = blockIdx.y;                                         // one grid row per expanded record
@@ -914,11 +916,13 @@ expand_classify_kernel(const uint32_t* __restrict__ records, uint32_t record_str
 	__shared__ uint32_t s_warp[kClassifyThreads / 32];
 	__shared__ uint32_t s_slot, s_ok;
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	if (t == 0) grid_dep_launch();                               // the work kernel may start its prologue
 	if (sig.n > 0 && blockIdx.x == 0 && blockIdx.y == 0 && t == 0) {
-		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank
+		// the update that precedes this kernel on the stream is complete, peer stores included: tell every rank.  (Launched
+		// programmatically — zn_exchange_expand — this is the one thread that waits for that update; a no-op otherwise.)
+		grid_dep_wait();
 		raise_flags(sig);
 	}
-	if (t == 0) grid_dep_launch();                               // the work kernel may start its prologue
 	uint32_t r = blockIdx.y;                                         // one grid row per expanded record
 	if (int(r) >= skip) r += uint32_t(skip_count);
 	if (r >= record_count) return;                                   // every record skipped: this launch only signals
