@@ -364,7 +364,12 @@ int zn_shard_scene_by_roots(const uint32_t* level_offsets, uint32_t level_count,
  *      zn_exchange_expand is asynchronous on the context stream: the launch raises this rank's flags for
  *      the last bound frame (everything before it on the stream is complete), waits on the device for
  *      the owners' flags of `frame` and derives their lists.  Expanding one frame behind leaves a frame of
- *      slack between ranks, so the flags are normally up and nothing spins.  Frames are expanded in order;
+ *      slack between ranks, so the flags are normally up and nothing spins.  The launch is PROGRAMMATIC: the
+ *      expansion of frame k-1 touches only exchange-owned buffers that the update of frame k does not (another
+ *      record slot, the other half of the lists), so its CTAs may start beside the tail of that update; only the
+ *      one thread that raises the flags waits for it, and everything enqueued after the expansion is ordered
+ *      behind both (ZN_EXCHANGE_EARLY_START=0 in the environment makes it a plain launch, for A/B runs).
+ *      Frames are expanded in order;
  *      a frame that was never bound (k - 1 = -1) or is already expanded is a no-op.
  *      index_bases[world*S] (host, may be NULL) is added to each record's indices.
  *      ZN_EXCHANGE_OVERLAP in desc.flags (opt-in): expansions run on the exchange's own low-priority side

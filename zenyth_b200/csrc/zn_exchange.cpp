@@ -24,7 +24,12 @@
 //     zn_exchange_bind(k); zn_scene_update of every owned scene; zn_exchange_expand(k-1).
 // The expansion launch raises this rank's flags for frame k (the update before it on the stream is
 // complete) and waits on the device for the peers' frame k-1 flags — which, one frame later, are
-// normally up already: the frame of slack absorbs jitter between ranks and no CTA spins.
+// normally up already: the frame of slack absorbs jitter between ranks and no CTA spins.  The launch is
+// programmatic (early_start in expand_visible_on): expand(k-1) shares nothing with update(k) — another
+// record slot, the other half of the lists — so its CTAs start beside the tail of update(k)'s emit kernel;
+// only the flag-raising thread executes griddepcontrol.wait, i.e. the flags still go up after update(k)
+// has completed, and the kernels after the expansion still wait for all of it (N = 2: 0.534 -> 0.529 ms,
+// N = 8: 0.590 -> 0.580 ms per frame).
 // Slot reuse.  Update(k+1) on rank r stores into slot (k+1) % 4 of every peer p.  It is
 // stream-ordered after r's expand(k-1), which waited for p's frame k-1 signal; p raised it in the
 // launch after its update(k-1), i.e. after its expand(k-3) was enqueued — so the youngest frame a

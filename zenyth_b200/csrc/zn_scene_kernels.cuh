@@ -779,6 +779,8 @@ constexpr int kExpandWarps = 8 * kExpandChunks;   // one 4-tile group per warp
 //   persistent warps, static stride over the groups, 1 or 8 items in flight per warp (LDGSTS ring)     39-41 / 80-84
 //   this structure, single speculative load round, L2-only (.cg) loads                                  39 / 68
 //   this structure, L1-cached header loads, masks fetched by mixed groups only (what is below)         36 / 64
+//   ... and the first-entity load (static table) ahead of the flag acquire and the header: 32 registers
+//   instead of 40, eight CTAs per SM (what is below)                                                   33 / 62
 // None of the coarser-grained or persistent forms beat a wide grid of small, short-lived warps: the
 // kernel is bound by how many independent 4 KiB store runs and scatters are in flight, and at f = 0.86
 // ncu shows the persistent form at 42% issue utilisation and 54% DRAM throughput with MIO / LSU
