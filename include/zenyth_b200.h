@@ -125,7 +125,7 @@ int zn_scene_destroy(zn_scene* scene);
  * Pageable arrays are staged by the driver before the call returns and may be reused at once;
  * page-locked arrays (zn_host_alloc) are read by the DMA engine later and must stay untouched until
  * the stream has passed the copy (zn_ctx_sync, or any synchronising read-back).
- * zn_scene_set_transforms of at most 16 entities — the handful a frame's game logic moved — is ONE kernel launch
+ * Either call for at most 16 entities — the handful a frame's game logic moved — is ONE kernel launch
  * that carries the values in its parameters (read before the call returns): no staging copy, no repack passes. */
 int zn_scene_set_transforms(zn_scene* scene, uint32_t first, uint32_t count,
                             const float* position, const float* rotation, const float* scale, size_t stride_bytes);

@@ -75,6 +75,30 @@ static int upload3(zn_scene* s, int row0, uint32_t first, uint32_t count, const 
 	return ZN_OK;
 }
 
+// A handful of entities (<= kPatchEntities): ONE launch carrying the values as kernel parameters — no staging copy, no
+// repack passes.  arrays[a] (NULL = absent) holds 3-float records for block rows row0 + 3a .. row0 + 3a + 2.
+static int patch_rows(zn_scene* s, uint32_t row0, uint32_t first, uint32_t count, const float* const* arrays, int n_arrays, size_t stride_bytes) {
+	PatchRows patch = {};
+	patch.count = count;
+	patch.row0 = row0;
+	for (int a = 0; a < n_arrays; ++a)
+		if (arrays[a]) patch.rows |= 0x7u << (3 * a);
+	if (count == 0 || patch.rows == 0u) return ZN_OK;
+	size_t l = 0;
+	for (uint32_t k = 0; k < count; ++k) {
+		const uint32_t i = first + k;
+		while (i >= s->levels[l].end) ++l;
+		const uint32_t rel = i - s->levels[l].begin;
+		patch.at[k] = (s->levels[l].tile_base + rel / kTile) * kBlockWords + rel % kTile;
+		for (int a = 0; a < n_arrays; ++a)
+			if (arrays[a]) std::memcpy(&patch.v[k][a * 3], reinterpret_cast<const uint8_t*>(arrays[a]) + size_t(k) * stride_bytes, 12);
+	}
+	s->inputs_touched = true;
+	patch_rows_kernel<<<1, kPatchEntities * 9, 0, s->ctx->stream>>>(s->blocks, patch);
+	ZN_CUDA(cudaGetLastError());
+	return ZN_OK;
+}
+
 // Download block rows [row0, row0+nrows) of entities [first, first+count) as packed [count][nrows].
 static int download_rows(zn_scene* s, int row0, int nrows, uint32_t first, uint32_t count, void* host) {
 	if (!host || count == 0) return ZN_OK;
@@ -228,25 +252,8 @@ int zn_scene_set_transforms(zn_scene* s, uint32_t first, uint32_t count, const f
 	if (rc != ZN_OK) return rc;
 	ZN_CUDA(cudaSetDevice(s->ctx->device));
 	if (count <= kPatchEntities && s->tile_count <= 0xFFFFFFFFu / kBlockWords) {
-		// a handful of moved entities: one launch carrying the values as parameters (no staging copy, no repack passes)
-		if (count == 0 || (!position && !rotation && !scale)) return ZN_OK;
-		PatchRows patch = {};
-		patch.count = count;
-		patch.rows = (position ? 0x007u : 0u) | (rotation ? 0x038u : 0u) | (scale ? 0x1C0u : 0u);
-		size_t l = 0;
-		for (uint32_t k = 0; k < count; ++k) {
-			const uint32_t i = first + k;
-			while (i >= s->levels[l].end) ++l;
-			const uint32_t rel = i - s->levels[l].begin;
-			patch.at[k] = (s->levels[l].tile_base + rel / kTile) * kBlockWords + rel % kTile;
-			const float* src[3] = {position, rotation, scale};
-			for (int a = 0; a < 3; ++a)
-				if (src[a]) std::memcpy(&patch.v[k][a * 3], reinterpret_cast<const uint8_t*>(src[a]) + size_t(k) * stride_bytes, 12);
-		}
-		s->inputs_touched = true;
-		patch_rows_kernel<<<1, kPatchEntities * 9, 0, s->ctx->stream>>>(s->blocks, patch);
-		ZN_CUDA(cudaGetLastError());
-		return ZN_OK;
+		const float* arrays[3] = {position, rotation, scale};
+		return patch_rows(s, 0, first, count, arrays, 3, stride_bytes);
 	}
 	if ((rc = upload3(s, 0, first, count, position, stride_bytes)) != ZN_OK) return rc;
 	if ((rc = upload3(s, 3, first, count, rotation, stride_bytes)) != ZN_OK) return rc;
@@ -258,6 +265,10 @@ int zn_scene_set_bounds(zn_scene* s, uint32_t first, uint32_t count, const float
 	if (rc == ZN_OK) rc = check_stride(stride_bytes, "zn_scene_set_bounds");
 	if (rc != ZN_OK) return rc;
 	ZN_CUDA(cudaSetDevice(s->ctx->device));
+	if (count <= kPatchEntities && s->tile_count <= 0xFFFFFFFFu / kBlockWords) {
+		const float* arrays[3] = {center, half_extent, nullptr};
+		return patch_rows(s, 9, first, count, arrays, 2, stride_bytes);
+	}
 	if ((rc = upload3(s, 9, first, count, center, stride_bytes)) != ZN_OK) return rc;
 	return upload3(s, 12, first, count, half_extent, stride_bytes);
 }

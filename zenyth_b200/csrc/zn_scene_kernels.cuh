@@ -1113,13 +1113,14 @@ __global__ void repack3_kernel(const uint32_t* __restrict__ src, uint32_t stride
 constexpr uint32_t kPatchEntities = 16;
 struct PatchRows {
 	uint32_t at[kPatchEntities];          // word offset of the entity's lane in row 0 of its block
-	float v[kPatchEntities][9];           // rows 0..8: position, rotation, scale
+	float v[kPatchEntities][9];           // up to nine consecutive block rows per entity
 	uint32_t count;
-	uint32_t rows;                        // bit r: row r is present
+	uint32_t row0;                        // v[e][r] belongs to block row row0 + r (0: position, rotation, scale; 9: AABB centre, half extent)
+	uint32_t rows;                        // bit r: v[e][r] is present
 };
 __global__ void patch_rows_kernel(uint32_t* __restrict__ blocks, const __grid_constant__ PatchRows patch) {
 	const uint32_t e = threadIdx.x / 9u, r = threadIdx.x % 9u;
-	if (e < patch.count && ((patch.rows >> r) & 1u)) blocks[size_t(patch.at[e]) + r * kTile] = __float_as_uint(patch.v[e][r]);
+	if (e < patch.count && ((patch.rows >> r) & 1u)) blocks[size_t(patch.at[e]) + (patch.row0 + r) * kTile] = __float_as_uint(patch.v[e][r]);
 }
 // One launch for a whole host frame (zn_scene_frame_host_submit): up to three packed [count][3]
 // arrays (position / rotation / scale, NULL = absent) of entities [first, first+count) into rows
