@@ -1,7 +1,7 @@
 // exchange_ranks.cpp — the multi-GPU host layer driven from C++ only: N processes (fork), a socket
 // hub as the host all-gather, Zenyth::PeerExchange over real CUDA IPC.  No torch, no NCCL, no Python.
 //
-//     exchange_ranks [world=2] [scenes_per_rank=1] [frames=9] [levels=7] [overlap=0]
+//     exchange_ranks [world=2] [scenes_per_rank=1] [frames=9] [levels=7] [overlap=0] [worklist=0]
 //
 // Rank r runs on GPU r % device_count, so with ONE GPU both ranks share cuda:0 (CUDA IPC between
 // processes on the same device is legal): IPC mapping, peer stores, flag stores and acquire loads
@@ -77,7 +77,7 @@ static CameraDesc camera_of_frame(int k) {
 	return c;
 }
 
-static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int levels, bool overlap, int fd) {
+static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int levels, bool overlap, bool worklist, int fd) {
 	try {
 		int devices = 0;
 		if (zn_device_count(&devices) != ZN_OK || devices < 1) { std::fprintf(stderr, "rank %u: no CUDA device\n", rank); return 3; }
@@ -114,6 +114,7 @@ static int rank_main(uint32_t rank, uint32_t world, uint32_t S, int frames, int 
 			scenes.push_back(std::make_unique<Scene>(ctx, desc));
 			detail::Check(zn_scene_fill_synthetic(scenes.back()->Handle(), 0x5A454E59u + 11u + mine[j], 8, 0.25f), "fill");
 			scenes.back()->SetIndexBase(bases[mine[j]]);
+			scenes.back()->SetExpandWorkList(worklist);   // the expansion strategy of the scene the exchange expands with
 			ptrs.push_back(scenes.back().get());
 		}
 		Channel ch{fd, world};
@@ -182,6 +183,7 @@ int main(int argc, char** argv) {
 	const int frames = argc > 3 ? std::atoi(argv[3]) : 9;
 	const int levels = argc > 4 ? std::atoi(argv[4]) : 7;
 	const bool overlap = argc > 5 && std::atoi(argv[5]) != 0;
+	const bool worklist = argc > 6 && std::atoi(argv[6]) != 0;
 	std::vector<int> hub_fds;
 	std::vector<pid_t> kids;
 	for (uint32_t r = 0; r < world; ++r) {
@@ -191,7 +193,7 @@ int main(int argc, char** argv) {
 		if (pid == 0) {
 			for (int fd : hub_fds) close(fd);
 			close(sv[0]);
-			std::exit(rank_main(r, world, S, frames, levels, overlap, sv[1]));
+			std::exit(rank_main(r, world, S, frames, levels, overlap, worklist, sv[1]));
 		}
 		close(sv[1]);
 		hub_fds.push_back(sv[0]);

@@ -219,13 +219,13 @@ def test_two_processes_exchange_over_peer_memory(tmp_path):
     assert out.stdout.count("peer exchange ok") == 2
 
 
-@pytest.mark.parametrize("world,scenes_per_rank,overlap", [(2, 1, 0), (2, 2, 0), (3, 1, 0), (2, 2, 1)])
-def test_cpp_ranks_exchange_without_torch_or_nccl(world, scenes_per_rank, overlap):
+@pytest.mark.parametrize("world,scenes_per_rank,overlap,worklist", [(2, 1, 0, 0), (2, 2, 0, 0), (3, 1, 0, 0), (2, 2, 1, 0), (2, 2, 0, 1), (2, 1, 1, 1)])
+def test_cpp_ranks_exchange_without_torch_or_nccl(world, scenes_per_rank, overlap, worklist):
     """tests/cpp/exchange_ranks.cpp: fork()ed C++ processes, a socket hub as the host all-gather, Zenyth::PeerExchange,
     ShardScenes and SceneIndexBases of include/zenyth_b200.hpp — every gathered list of every frame is checked
     against the single-GPU result inside the program.  Ranks land on GPU rank % device_count."""
     from zenyth_b200 import build as zb
     exe = zb.build_cpp_tests()
-    out = subprocess.run([exe, str(world), str(scenes_per_rank), "9", "7", str(overlap)], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, str(world), str(scenes_per_rank), "9", "7", str(overlap), str(worklist)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert out.stdout.count("exchange ok rank") == world
