@@ -430,7 +430,7 @@ scene_top_kernel(const __grid_constant__ TopMaps maps, const __grid_constant__ F
 constexpr uint32_t kAabbBytes = 6u * kTile * 4u;
 constexpr uint32_t kCullSmem = 2u * kTile * 64u + kAabbBytes + 1024u;
 
-__global__ void __launch_bounds__(kTile, 4)
+__global__ void __launch_bounds__(kTile, 5)
 scene_cull_kernel(const __grid_constant__ CUtensorMap tm_world, const __grid_constant__ CUtensorMap tm_mvp,
                   const __grid_constant__ FrameConst fc, const uint32_t* __restrict__ blocks,
                   const uint32_t* __restrict__ tile_first_entity, uint32_t tiles, uint32_t entity_count,
