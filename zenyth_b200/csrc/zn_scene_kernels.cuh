@@ -4,10 +4,15 @@
 //   scene_level_kernel<HAS_PARENT>  one launch per hierarchy level (K1/K2 of SURVEY.md §2):
 //       TRS -> local -> world (= parent.world * local) -> MVP -> AABB-vs-frustum flag, plus the
 //       tile's 256-bit visibility mask.
+//   scene_top_kernel                the leading levels whose tiles fit one CTA's shared memory, in ONE launch in
+//       place of level 0: parents are read from the shared tiles, not through L2.
+//   scene_cull_kernel               one camera pass over existing world matrices (zn_scene_cull).
 //   emit_visible_kernel             one launch per frame (K3): ordered visible list from the masks,
 //       single pass — a chunk's base is the sum of the chunk totals before it, then an ascending
 //       warp-cooperative scatter; also fills the header of the frame's visibility record.
-//   expand_visible_kernel           multi-GPU: all-gathered visibility records -> every rank's list.
+//   expand_visible_kernel           multi-GPU: all-gathered visibility records -> every rank's list
+//       (expand_classify_kernel + expand_work_kernel: the same through a work list, for sparse sets).
+//   patch_rows_kernel / repack*     uploads: a handful of entities as kernel parameters, ranges through staging.
 //
 // scene_level_kernel is PERSISTENT (4 CTAs of 256 threads per SM, tiles claimed by atomic ticket)
 // and software-pipelined with the TMA unit:
